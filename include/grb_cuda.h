@@ -1,0 +1,203 @@
+/* grb_cuda.h -- C ABI of libgrb_cuda.so, the B200-native GraphBLAS semiring engine.
+ *
+ * This is the drop-in boundary: the entry points are the subset of the
+ * GraphBLAS C API 2.0 that python-graphblas's "vanilla" backend consumes for the
+ * GrB_mxm / GrB_mxv / GrB_vxm path, with the same names, argument order and GrB_Info
+ * convention, so the reference's dispatcher
+ *
+ *     graphblas/core/base.py:23-54   call(cfunc_name, args) -> getattr(lib, cfunc_name)(*cargs)
+ *
+ * can bind them unchanged (binding shown in INTEGRATION.md).  Plain pointers and sizes only;
+ * no torch / C++ types.  All index arrays crossing this boundary are GrB_Index (uint64_t)
+ * exactly as the reference hands them over (graphblas/core/utils.py:58-69).
+ *
+ * Each declaration cites the reference call site it serves.
+ */
+#ifndef GRB_CUDA_H
+#define GRB_CUDA_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t GrB_Index;
+
+/* GrB_Info values: GraphBLAS C API 2.0; consumed by graphblas/exceptions.py:123-157 */
+typedef enum {
+    GrB_SUCCESS = 0,
+    GrB_NO_VALUE = 1,
+    GrB_UNINITIALIZED_OBJECT = -1,
+    GrB_NULL_POINTER = -2,
+    GrB_INVALID_VALUE = -3,
+    GrB_INVALID_INDEX = -4,
+    GrB_DOMAIN_MISMATCH = -5,
+    GrB_DIMENSION_MISMATCH = -6,
+    GrB_OUTPUT_NOT_EMPTY = -7,
+    GrB_NOT_IMPLEMENTED = -8,
+    GrB_PANIC = -101,
+    GrB_OUT_OF_MEMORY = -102,
+    GrB_INSUFFICIENT_SPACE = -103,
+    GrB_INVALID_OBJECT = -104,
+    GrB_INDEX_OUT_OF_BOUNDS = -105,
+    GrB_EMPTY_OBJECT = -106
+} GrB_Info;
+
+typedef enum { GrB_NONBLOCKING = 0, GrB_BLOCKING = 1 } GrB_Mode;
+typedef enum { GrB_COMPLETE = 0, GrB_MATERIALIZE = 1 } GrB_WaitMode;
+typedef enum { GrB_CSR_FORMAT = 0, GrB_CSC_FORMAT = 1, GrB_COO_FORMAT = 2 } GrB_Format;
+typedef enum { GrB_OUTP = 0, GrB_MASK = 1, GrB_INP0 = 2, GrB_INP1 = 3 } GrB_Desc_Field;
+typedef enum { GrB_DEFAULT = 0, GrB_REPLACE = 1, GrB_COMP = 2, GrB_TRAN = 3, GrB_STRUCTURE = 4 } GrB_Desc_Value;
+
+/* opaque handles (graphblas/core/matrix.py:196 holds them in 1-element cells) */
+typedef struct GrB_Type_opaque *GrB_Type;
+typedef struct GrB_UnaryOp_opaque *GrB_UnaryOp;
+typedef struct GrB_BinaryOp_opaque *GrB_BinaryOp;
+typedef struct GrB_Monoid_opaque *GrB_Monoid;
+typedef struct GrB_Semiring_opaque *GrB_Semiring;
+typedef struct GrB_Descriptor_opaque *GrB_Descriptor;
+typedef struct GrB_Matrix_opaque *GrB_Matrix;
+typedef struct GrB_Vector_opaque *GrB_Vector;
+
+/* ------------------------------------------------------------------ context
+ * graphblas/__init__.py:143,158-173 initialize(blocking=...), is_initialized() */
+GrB_Info GrB_init(GrB_Mode mode);
+GrB_Info GrB_finalize(void);
+GrB_Info GrB_getVersion(unsigned int *version, unsigned int *subversion);
+
+/* ------------------------------------------------------------------ builtin objects
+ * Every builtin type / operator / monoid / semiring / descriptor is also exported as a data
+ * symbol with its C-API name (GrB_INT64, GrB_PLUS_TIMES_SEMIRING_FP32, GxB_ANY_PAIR_INT64,
+ * GrB_DESC_RSC, ...) because the reference's operator registry discovers them by scanning
+ * dir(lib) (graphblas/core/operator/base.py:690,803-893; semiring.py:185-219).
+ * GrB_cuda_lookup returns the same handle by name (NULL if unknown); GrB_cuda_symbol_names
+ * fills a NUL-separated list (returns required size) so a binding can enumerate them. */
+void *GrB_cuda_lookup(const char *name);
+size_t GrB_cuda_symbol_names(char *buf, size_t buflen);
+
+extern GrB_Type GrB_BOOL, GrB_INT8, GrB_INT16, GrB_INT32, GrB_INT64, GrB_UINT8, GrB_UINT16, GrB_UINT32,
+    GrB_UINT64, GrB_FP32, GrB_FP64;
+
+/* ------------------------------------------------------------------ Matrix lifecycle
+ * graphblas/core/matrix.py:190-203 (new), :218-225 (free), :482-494 (nvals), :764-789 (wait) */
+GrB_Info GrB_Matrix_new(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols);
+GrB_Info GrB_Matrix_free(GrB_Matrix *A);
+GrB_Info GrB_Matrix_dup(GrB_Matrix *C, const GrB_Matrix A);
+GrB_Info GrB_Matrix_clear(GrB_Matrix A);
+GrB_Info GrB_Matrix_nrows(GrB_Index *nrows, const GrB_Matrix A);
+GrB_Info GrB_Matrix_ncols(GrB_Index *ncols, const GrB_Matrix A);
+GrB_Info GrB_Matrix_nvals(GrB_Index *nvals, const GrB_Matrix A);
+GrB_Info GrB_Matrix_wait(GrB_Matrix A, GrB_WaitMode mode);
+GrB_Info GrB_Matrix_error(const char **error, const GrB_Matrix A); /* graphblas/exceptions.py:171-189 */
+
+/* ------------------------------------------------------------------ Vector lifecycle
+ * graphblas/core/vector.py:159-170 (new), :184-191 (free) */
+GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n);
+GrB_Info GrB_Vector_free(GrB_Vector *v);
+GrB_Info GrB_Vector_dup(GrB_Vector *w, const GrB_Vector u);
+GrB_Info GrB_Vector_clear(GrB_Vector v);
+GrB_Info GrB_Vector_size(GrB_Index *n, const GrB_Vector v);
+GrB_Info GrB_Vector_nvals(GrB_Index *nvals, const GrB_Vector v);
+GrB_Info GrB_Vector_wait(GrB_Vector v, GrB_WaitMode mode);
+GrB_Info GrB_Vector_error(const char **error, const GrB_Vector v);
+
+/* ------------------------------------------------------------------ the hot path
+ * GrB_mxm : graphblas/core/matrix.py:2319-2328 (and core/vector.py:1778-1786 outer)
+ * GrB_mxv : graphblas/core/matrix.py:2252-2259
+ * GrB_vxm : graphblas/core/vector.py:1368-1375 (and :1734-1741 inner)
+ * argument list assembled at graphblas/core/base.py:496-503:  [C, mask, accum, op, A, B, desc] */
+GrB_Info GrB_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Semiring op,
+                 const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc);
+GrB_Info GrB_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring op,
+                 const GrB_Matrix A, const GrB_Vector u, const GrB_Descriptor desc);
+GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring op,
+                 const GrB_Vector u, const GrB_Matrix A, const GrB_Descriptor desc);
+
+/* ------------------------------------------------------------------ O(n) vector operations that keep
+ * BFS / SSSP / PageRank iterations on the device
+ * eWiseAdd/eWiseMult: graphblas/core/vector.py:1050-1055,1142 ; apply: core/matrix.py:2440-2533 ;
+ * reduce: core/vector.py:1669-1681 ; assign scalar under mask: core/vector.py:2020-2035 */
+GrB_Info GrB_Vector_eWiseAdd_BinaryOp(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum,
+                                      const GrB_BinaryOp op, const GrB_Vector u, const GrB_Vector v,
+                                      const GrB_Descriptor desc);
+GrB_Info GrB_Vector_eWiseMult_BinaryOp(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum,
+                                       const GrB_BinaryOp op, const GrB_Vector u, const GrB_Vector v,
+                                       const GrB_Descriptor desc);
+GrB_Info GrB_Vector_apply(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_UnaryOp op,
+                          const GrB_Vector u, const GrB_Descriptor desc);
+/* reduce to a C scalar with a monoid; *nvals_out (optional) receives u's nvals so the caller can tell
+ * "empty" (GrB_Vector_reduce_T leaves *val untouched then).  val is accum'ed when accum != NULL. */
+GrB_Info GrB_cuda_Vector_reduce(void *val, GrB_Type val_type, const GrB_BinaryOp accum, const GrB_Monoid op,
+                                const GrB_Vector u, GrB_Index *nvals_out);
+/* w<mask>(all) = accum(w, scalar): GrB_Vector_assign_T with GrB_ALL */
+GrB_Info GrB_cuda_Vector_assign_scalar(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum,
+                                       const void *val, GrB_Type val_type, const GrB_Descriptor desc);
+
+/* ------------------------------------------------------------------ data in / out (type-generic cores;
+ * the typed C-API names GrB_Matrix_import_FP32 ... are exported too and forward to these)
+ * import/export: graphblas/core/matrix.py:992-1068, :1601-1645 ; build: :627-681 ;
+ * extractTuples: :525-594 ; Vector build/extractTuples: core/vector.py:465-568 */
+GrB_Info GrB_cuda_Matrix_import(GrB_Matrix *A, GrB_Type type, GrB_Type xtype /* type of Ax; NULL = type */,
+                                GrB_Index nrows, GrB_Index ncols,
+                                const GrB_Index *Ap, const GrB_Index *Ai, const void *Ax, GrB_Index Ap_len,
+                                GrB_Index Ai_len, GrB_Index Ax_len, GrB_Format format);
+GrB_Info GrB_Matrix_exportSize(GrB_Index *Ap_len, GrB_Index *Ai_len, GrB_Index *Ax_len, GrB_Format format,
+                               GrB_Matrix A);
+GrB_Info GrB_cuda_Matrix_export(GrB_Index *Ap, GrB_Index *Ai, void *Ax, GrB_Type type, GrB_Index *Ap_len,
+                                GrB_Index *Ai_len, GrB_Index *Ax_len, GrB_Format format, GrB_Matrix A);
+GrB_Info GrB_cuda_Matrix_build(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const void *X,
+                               GrB_Type xtype, GrB_Index nvals, const GrB_BinaryOp dup);
+GrB_Info GrB_cuda_Matrix_extractTuples(GrB_Index *I, GrB_Index *J, void *X, GrB_Type xtype, GrB_Index *nvals,
+                                       const GrB_Matrix A);
+GrB_Info GrB_cuda_Matrix_extractElement(void *x, GrB_Type xtype, const GrB_Matrix A, GrB_Index i, GrB_Index j);
+GrB_Info GrB_cuda_Vector_build(GrB_Vector w, const GrB_Index *I, const void *X, GrB_Type xtype, GrB_Index nvals,
+                               const GrB_BinaryOp dup);
+GrB_Info GrB_cuda_Vector_extractTuples(GrB_Index *I, void *X, GrB_Type xtype, GrB_Index *nvals,
+                                       const GrB_Vector v);
+GrB_Info GrB_cuda_Vector_setElement(GrB_Vector w, const void *x, GrB_Type xtype, GrB_Index i);
+GrB_Info GrB_cuda_Vector_extractElement(void *x, GrB_Type xtype, const GrB_Vector v, GrB_Index i);
+GrB_Info GrB_Vector_removeElement(GrB_Vector w, GrB_Index i);
+
+/* ------------------------------------------------------------------ device-side extensions (the GxB_ analogue;
+ * precedent: graphblas/core/ss/descriptor.py:77-83 axb_method, ss/_core.py:129-138 gpu_id) */
+/* fast import with the device's own index widths (int64 row pointers, int32 column indices); `on_device`
+ * != 0 means the three pointers are device pointers (copied, not adopted) */
+GrB_Info GrB_cuda_Matrix_import_csr32(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols,
+                                      const int64_t *Ap, const int32_t *Aj, const void *Ax, GrB_Index nvals,
+                                      int on_device, int sorted);
+GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void *Ax, GrB_Index nvals_capacity,
+                                      GrB_Matrix A, int sort);
+/* raw device views (valid until the object is next modified) */
+GrB_Info GrB_cuda_Matrix_device_csr(const GrB_Matrix A, int64_t **Ap, int32_t **Aj, void **Ax);
+GrB_Info GrB_cuda_Vector_device_arrays(const GrB_Vector v, void **vals, uint8_t **present);
+GrB_Info GrB_cuda_Vector_import_dense(GrB_Vector *v, GrB_Type type, GrB_Index n, const void *vals,
+                                      const uint8_t *present /* NULL = full */, int on_device);
+GrB_Info GrB_cuda_Vector_export_dense(void *vals, uint8_t *present, const GrB_Vector v);
+GrB_Info GrB_cuda_Vector_touch(GrB_Vector v); /* arrays were modified through device_arrays(): drop caches */
+GrB_Info GrB_cuda_Matrix_sort(GrB_Matrix A);          /* finish a lazily "jumbled" result now */
+GrB_Info GrB_cuda_Matrix_build_transpose(GrB_Matrix A); /* prebuild + cache the CSR of A' */
+/* mxm symbolic phase only: *flops, *nvals_out of A(+).(x)B without forming it */
+GrB_Info GrB_cuda_mxm_symbolic(GrB_Index *flops, GrB_Index *nvals_out, const GrB_Matrix A, const GrB_Matrix B,
+                               const GrB_Descriptor desc);
+
+/* streams / timing / options / introspection */
+GrB_Info GrB_cuda_set_stream(void *cuda_stream); /* NULL restores the library's own stream */
+void *GrB_cuda_get_stream(void);
+GrB_Info GrB_cuda_sync(void);
+GrB_Info GrB_cuda_set_device(int device);
+GrB_Info GrB_cuda_timer_start(void);          /* cudaEventRecord on the library stream */
+GrB_Info GrB_cuda_timer_stop(float *ms);      /* record + synchronize + elapsed */
+GrB_Info GrB_cuda_set_option(const char *key, const char *value);
+const char *GrB_cuda_get_option(const char *key);
+uint64_t GrB_cuda_launch_count(void);         /* kernels launched by this library so far */
+GrB_Info GrB_cuda_kernel_time(const char *name, double *total_ms, uint64_t *launches); /* when option profile=1 */
+size_t GrB_cuda_memory_in_use(void);
+const char *GrB_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRB_CUDA_H */

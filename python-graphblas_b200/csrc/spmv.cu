@@ -1,0 +1,528 @@
+// spmv.cu -- t = M (+).(x) u for GrB_mxv / GrB_vxm, M = A or A'.
+//
+//  pull  (M rows available as CSR):  merge-path CSR SpMV.  One CTA consumes a fixed-size slice of the
+//        merge of (row-end offsets, nonzero indices); products are gathered with coalesced loads into
+//        shared memory, each thread then walks its own equal share of the merge path and emits finished
+//        rows; partial rows are stitched with a warp-shuffle segmented (reduce-by-key) scan inside the
+//        CTA and a tiny fix-up kernel across CTAs.  Load balance is independent of the degree skew
+//        (R-MAT max degree 97k vs mean 16).  Algorithmic bytes: nnz*(4 + rho*s_val) + (nrows+1)*8 +
+//        ncols*s_x + nrows*(s_y+1)   (SURVEY.md section 8d).
+//  pull  (masked): warp-per-row kernel that skips rows the mask rules out and, for the ANY monoid,
+//        stops at the first hit (bottom-up BFS step).
+//  push  (only CSR of M' available, u sparse): frontier compaction + warp-per-frontier-vertex scatter with
+//        atomic monoid combine; the mask is tested in-register before the atomic.
+//
+// Serves: GrB_mxv (reference core/matrix.py:2252-2259), GrB_vxm (core/vector.py:1368-1375).
+#include <limits.h>
+
+#include "grb_ops.cuh"
+
+constexpr int SPMV_BLOCK = 256;
+
+template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? 6 : 8); };
+
+// ---- shuffle helpers for arbitrary 1..8 byte value types ----
+template <typename T> __device__ __forceinline__ T shfl_up_any(T v, int delta) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        b = __shfl_up_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, 8);
+        return v;
+    } else {
+        unsigned int b = 0;
+        memcpy(&b, &v, sizeof(T));
+        b = __shfl_up_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, sizeof(T));
+        return v;
+    }
+}
+template <typename T> __device__ __forceinline__ T shfl_down_any(T v, int delta) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        b = __shfl_down_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, 8);
+        return v;
+    } else {
+        unsigned int b = 0;
+        memcpy(&b, &v, sizeof(T));
+        b = __shfl_down_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, sizeof(T));
+        return v;
+    }
+}
+
+// (row, value, has) triple of a partially reduced row; combine = reduce-by-key, associative
+template <typename T> struct Carry { int row; int has; T val; };
+template <typename SR, typename T>
+__device__ __forceinline__ Carry<T> carry_combine(const SR &sr, const Carry<T> &a, const Carry<T> &b) {
+    Carry<T> r = b;
+    if (a.row == b.row && a.has) {
+        r.val = b.has ? sr.add(a.val, b.val) : a.val;
+        r.has = 1;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ merge-path tile search
+__global__ void merge_search_kernel(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t nnz, int tile_items,
+                                    int64_t n_tiles, int64_t *__restrict__ tile_starts) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    int64_t diag = t * (int64_t)tile_items;
+    if (diag > nrows + nnz) diag = nrows + nnz;
+    int64_t lo = diag > nnz ? diag - nnz : 0;
+    int64_t hi = diag < nrows ? diag : nrows;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid + 1] <= diag - mid - 1) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_starts[t] = lo;
+}
+
+// ------------------------------------------------------------------ merge-path SpMV
+template <typename SR, typename T, bool XFULL>
+__global__ void __launch_bounds__(SPMV_BLOCK)
+spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__ rowptr,
+                  const int32_t *__restrict__ colidx, const T *__restrict__ avals, const T *__restrict__ x,
+                  const uint8_t *__restrict__ xp, const int64_t *__restrict__ tile_starts, bool flip,
+                  T *__restrict__ t_vals, uint8_t *__restrict__ t_present, int64_t *__restrict__ carry_row,
+                  T *__restrict__ carry_val, uint8_t *__restrict__ carry_has) {
+    constexpr int IPT = SpmvCfg<T>::IPT;
+    constexpr int TILE = SPMV_BLOCK * IPT;
+    __shared__ int s_rowend[TILE + 1];
+    __shared__ T s_prod[TILE];
+    __shared__ uint8_t s_has[XFULL ? 1 : TILE];
+    __shared__ Carry<T> s_warp[SPMV_BLOCK / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t total = nrows + nnz;
+    const int64_t diag0 = tile * (int64_t)TILE;
+    const int64_t diag1 = (diag0 + TILE < total) ? diag0 + TILE : total;
+    const int64_t r0 = tile_starts[tile], r1 = tile_starts[tile + 1];
+    const int64_t k0 = diag0 - r0, k1 = diag1 - r1;
+    const int tile_rows = (int)(r1 - r0), tile_nnz = (int)(k1 - k0);
+    const int tile_items = tile_rows + tile_nnz;
+
+    for (int i = tid; i < tile_rows; i += SPMV_BLOCK) s_rowend[i] = (int)(rowptr[r0 + i + 1] - k0);
+    if (tid == 0) s_rowend[tile_rows] = INT_MAX;
+
+    // coalesced gather phase: all loads of the unrolled batch are issued before any use
+    {
+        int32_t c[IPT];
+        T a[IPT];
+#pragma unroll
+        for (int it = 0; it < IPT; it++) {
+            int idx = tid + it * SPMV_BLOCK;
+            c[it] = 0;
+            if (idx < tile_nnz) {
+                c[it] = colidx[k0 + idx];
+                if (sr.reads_a()) a[it] = avals[k0 + idx];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < IPT; it++) {
+            int idx = tid + it * SPMV_BLOCK;
+            if (idx < tile_nnz) {
+                T av = sr.reads_a() ? a[it] : one_of<T>();
+                T xv = sr.reads_b() ? x[c[it]] : one_of<T>();
+                s_prod[idx] = flip ? sr.mul(xv, av) : sr.mul(av, xv);
+                if (!XFULL) s_has[idx] = xp[c[it]];
+            }
+        }
+    }
+    __syncthreads();
+
+    // each thread's share of the merge path
+    int d = tid * IPT;
+    if (d > tile_items) d = tile_items;
+    int lo = d > tile_nnz ? d - tile_nnz : 0;
+    int hi = d < tile_rows ? d : tile_rows;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_rowend[mid] <= d - mid - 1) lo = mid + 1;
+        else hi = mid;
+    }
+    int xr = lo, yk = d - lo;
+    const int x_first = xr;
+    T emit_val[IPT];          // indexed by the (static) step at which the row ended
+    unsigned emit_mask = 0, emit_has = 0;
+    T acc = sr.identity();
+    int has = 0;
+#pragma unroll
+    for (int it = 0; it < IPT; it++) {
+        emit_val[it] = acc;
+        if (d + it < tile_items) {
+            if (yk < s_rowend[xr]) {
+                bool ph = XFULL ? true : (s_has[yk] != 0);
+                if (ph) {
+                    acc = has ? sr.add(acc, s_prod[yk]) : s_prod[yk];
+                    has = 1;
+                }
+                yk++;
+            } else {
+                emit_val[it] = acc;
+                emit_mask |= 1u << it;
+                emit_has |= (unsigned)has << it;
+                xr++;
+                acc = sr.identity();
+                has = 0;
+            }
+        }
+    }
+
+    // segmented inclusive scan of the per-thread leftovers (key = row)
+    Carry<T> cur;
+    cur.row = xr;
+    cur.has = has;
+    cur.val = acc;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Carry<T> up;
+        up.row = __shfl_up_sync(0xffffffffu, cur.row, o);
+        up.has = __shfl_up_sync(0xffffffffu, cur.has, o);
+        up.val = shfl_up_any(cur.val, o);
+        if (lane >= o) cur = carry_combine(sr, up, cur);
+    }
+    if (lane == 31) s_warp[warp] = cur;
+    __syncthreads();
+    if (warp == 0) {
+        Carry<T> w;
+        if (lane < SPMV_BLOCK / 32) w = s_warp[lane];
+        else { w.row = -1; w.has = 0; w.val = sr.identity(); }
+#pragma unroll
+        for (int o = 1; o < SPMV_BLOCK / 32; o <<= 1) {
+            Carry<T> up;
+            up.row = __shfl_up_sync(0xffffffffu, w.row, o);
+            up.has = __shfl_up_sync(0xffffffffu, w.has, o);
+            up.val = shfl_up_any(w.val, o);
+            if (lane >= o) w = carry_combine(sr, up, w);
+        }
+        if (lane < SPMV_BLOCK / 32) s_warp[lane] = w;
+    }
+    __syncthreads();
+    // exclusive prefix for this thread
+    Carry<T> prev;
+    prev.row = __shfl_up_sync(0xffffffffu, cur.row, 1);
+    prev.has = __shfl_up_sync(0xffffffffu, cur.has, 1);
+    prev.val = shfl_up_any(cur.val, 1);
+    if (lane == 0) { prev.row = -1; prev.has = 0; prev.val = sr.identity(); }
+    if (warp > 0) {
+        Carry<T> wp = s_warp[warp - 1];
+        prev = (lane == 0) ? wp : carry_combine(sr, wp, prev);
+    }
+    // write finished rows; the first one may continue a row begun by earlier threads of this tile
+#pragma unroll
+    for (int it = 0; it < IPT; it++) {
+        if (emit_mask & (1u << it)) {
+            const int e = __popc(emit_mask & ((1u << it) - 1u));
+            T v = emit_val[it];
+            int h = (emit_has >> it) & 1;
+            if (e == 0 && prev.row == x_first && prev.has) {
+                v = h ? sr.add(prev.val, v) : prev.val;
+                h = 1;
+            }
+            const int64_t row = r0 + x_first + e;
+            t_vals[row] = h ? v : sr.identity();
+            t_present[row] = (uint8_t)h;
+        }
+    }
+    // tile carry-out: partial sum of the row that continues into the next tile
+    if (tid == SPMV_BLOCK - 1) {
+        Carry<T> tot = (warp > 0) ? carry_combine(sr, s_warp[warp - 1], cur) : cur;
+        // `cur` is warp-inclusive; combining with the previous warps' total gives the block-inclusive value
+        carry_row[tile] = r0 + tot.row;
+        carry_val[tile] = tot.val;
+        carry_has[tile] = (uint8_t)tot.has;
+    }
+}
+
+// cross-tile fix-up: the last tile that carries into a row folds the whole chain of carries into it
+template <typename SR, typename T>
+__global__ void spmv_merge_fixup_kernel(SR sr, int64_t n_tiles, int64_t nrows, const int64_t *__restrict__ carry_row,
+                                        const T *__restrict__ carry_val, const uint8_t *__restrict__ carry_has,
+                                        T *__restrict__ t_vals, uint8_t *__restrict__ t_present) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int64_t row = carry_row[t];
+    if (row >= nrows) return;
+    if (t + 1 < n_tiles && carry_row[t + 1] == row) return;  // a later tile owns this chain
+    T acc = sr.identity();
+    int has = 0;
+    for (int64_t q = t; q >= 0 && carry_row[q] == row; q--) {
+        if (carry_has[q]) {
+            acc = has ? sr.add(carry_val[q], acc) : carry_val[q];
+            has = 1;
+        }
+    }
+    if (!has) return;
+    if (t_present[row]) t_vals[row] = sr.add(acc, t_vals[row]);
+    else { t_vals[row] = acc; t_present[row] = 1; }
+}
+
+// ------------------------------------------------------------------ warp-per-row pull with mask skip / ANY early exit
+template <typename SR, typename T, bool XFULL>
+__global__ void __launch_bounds__(256)
+spmv_rowwarp_kernel(SR sr, int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                    const T *__restrict__ avals, const T *__restrict__ x, const uint8_t *__restrict__ xp, bool flip,
+                    const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
+                    uint8_t *__restrict__ t_present) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w; i < nrows; i += nw) {
+        if (mask) {
+            bool m = (mask[i] != 0) != mask_comp;
+            if (!m) {  // the write-back will discard T(i) anyway
+                if (lane == 0) { t_present[i] = 0; t_vals[i] = sr.identity(); }
+                continue;
+            }
+        }
+        const int64_t b = rowptr[i], e = rowptr[i + 1];
+        T acc = sr.identity();
+        int has = 0;
+        for (int64_t k = b + lane; k < e; k += 32) {
+            int32_t c = colidx[k];
+            bool ph = XFULL ? true : (xp[c] != 0);
+            if (ph) {
+                T av = sr.reads_a() ? avals[k] : one_of<T>();
+                T xv = sr.reads_b() ? x[c] : one_of<T>();
+                T p = flip ? sr.mul(xv, av) : sr.mul(av, xv);
+                acc = has ? sr.add(acc, p) : p;
+                has = 1;
+            }
+            if (SR::kAddIsAny && __any_sync(__activemask(), has)) break;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T ov = shfl_down_any(acc, o);
+            int oh = __shfl_down_sync(0xffffffffu, has, o);
+            if (oh) {
+                acc = has ? sr.add(acc, ov) : ov;
+                has = 1;
+            }
+        }
+        if (lane == 0) {
+            t_vals[i] = has ? acc : sr.identity();
+            t_present[i] = (uint8_t)has;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ push (SpMSpV)
+__global__ void compact_present_kernel(const uint8_t *__restrict__ present, int64_t n, int32_t *__restrict__ out,
+                                       unsigned long long *__restrict__ counter) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = i - lane; base < n; base += stride) {
+        int64_t k = base + lane;
+        bool p = k < n && present[k] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, p);
+        if (bal) {
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(counter, (unsigned long long)__popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (p) out[pos + __popc(bal & ((1u << lane) - 1))] = (int32_t)k;
+        }
+    }
+}
+
+template <typename T> __global__ void fill_value_kernel(T *__restrict__ p, T v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+template <typename SR, typename T>
+__global__ void __launch_bounds__(256)
+spmspv_push_kernel(SR sr, const int32_t *__restrict__ frontier, int64_t n_frontier, const int64_t *__restrict__ rowptr,
+                   const int32_t *__restrict__ colidx, const T *__restrict__ avals, const T *__restrict__ u, bool flip,
+                   const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
+                   uint8_t *__restrict__ t_present) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t f = w; f < n_frontier; f += nw) {
+        const int32_t i = frontier[f];
+        const T uv = sr.reads_b() ? u[i] : one_of<T>();
+        const int64_t b = rowptr[i], e = rowptr[i + 1];
+        for (int64_t k = b + lane; k < e; k += 32) {
+            int32_t j = colidx[k];
+            if (mask && ((mask[j] != 0) == mask_comp)) continue;  // mask applied in-register before the write
+            T av = sr.reads_a() ? avals[k] : one_of<T>();
+            T p = flip ? sr.mul(uv, av) : sr.mul(av, uv);
+            if (SR::kAddIsAny && !sr.reads_a() && !sr.reads_b()) {
+                t_present[j] = 1;  // any_pair: value is the constant 1 written by the fill
+            } else {
+                atomic_combine(sr, &t_vals[j], p);
+                t_present[j] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static GrB_Info ensure_tiles(CsrArrays &c, int64_t nrows, int64_t nnz, int tile_items, std::string *err) {
+    if (c.tile_starts && c.tile_items == tile_items) return GrB_SUCCESS;
+    dev_free(c.tile_starts);
+    c.tile_starts = nullptr;
+    int64_t n_tiles = (nrows + nnz + tile_items - 1) / tile_items;
+    c.tile_starts = dev_alloc_t<int64_t>((size_t)n_tiles + 1);
+    if (!c.tile_starts) return set_error(err, GrB_OUT_OF_MEMORY, "merge-path tile table");
+    c.n_tiles = n_tiles;
+    c.tile_items = tile_items;
+    LAUNCH_NOTE("merge_search");
+    merge_search_kernel<<<(unsigned)((n_tiles + 1 + 255) / 256), 256, 0, g_stream>>>(c.ptr, nrows, nnz, tile_items, n_tiles,
+                                                                                 c.tile_starts);
+    CUDA_TRY(err, cudaGetLastError());
+    return GrB_SUCCESS;
+}
+
+template <typename SR, typename T>
+static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz, const T *avals, const T *x,
+                         const uint8_t *xp, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
+                         uint8_t *t_present, std::string *err) {
+    if (mrows == 0) return GrB_SUCCESS;
+    const char *method = opt_get("spmv", "auto");
+    bool use_rowwarp = !strcmp(method, "rowwarp") || (!strcmp(method, "auto") && mask != nullptr);
+    if (use_rowwarp) {
+        int64_t warps_needed = mrows;
+        int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)g_num_sms * 32);
+        LAUNCH_NOTE("spmv_rowwarp");
+        if (xp) spmv_rowwarp_kernel<SR, T, false><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present);
+        else spmv_rowwarp_kernel<SR, T, true><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present);
+        CUDA_TRY(err, cudaGetLastError());
+        return GrB_SUCCESS;
+    }
+    constexpr int TILE = SPMV_BLOCK * SpmvCfg<T>::IPT;
+    GRB_TRY(ensure_tiles(M, mrows, nnz, TILE, err));
+    const int64_t n_tiles = M.n_tiles;
+    int64_t *carry_row = dev_alloc_t<int64_t>((size_t)n_tiles);
+    T *carry_val = dev_alloc_t<T>((size_t)n_tiles);
+    uint8_t *carry_has = dev_alloc_t<uint8_t>((size_t)n_tiles);
+    if (!carry_row || !carry_val || !carry_has) {
+        dev_free(carry_row); dev_free(carry_val); dev_free(carry_has);
+        return set_error(err, GrB_OUT_OF_MEMORY, "merge-path carry arrays");
+    }
+    {
+        LAUNCH_NOTE("spmv_merge");
+        if (xp) spmv_merge_kernel<SR, T, false><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has);
+        else spmv_merge_kernel<SR, T, true><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has);
+    }
+    {
+        LAUNCH_NOTE("spmv_merge_fixup");
+        spmv_merge_fixup_kernel<SR, T><<<(unsigned)((n_tiles + 255) / 256), 256, 0, g_stream>>>(sr, n_tiles, mrows, carry_row, carry_val, carry_has, t_vals, t_present);
+    }
+    cudaError_t e = cudaGetLastError();
+    dev_free(carry_row); dev_free(carry_val); dev_free(carry_has);
+    CUDA_TRY(err, e);
+    return GrB_SUCCESS;
+}
+
+template <typename SR, typename T>
+static GrB_Info run_push(const SR &sr, const CsrArrays &A, int64_t arows, int64_t out_len, const T *avals, const T *u,
+                         const uint8_t *up, int64_t u_nvals, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
+                         uint8_t *t_present, std::string *err) {
+    CUDA_TRY(err, cudaMemsetAsync(t_present, 0, (size_t)(out_len > 0 ? out_len : 1), g_stream));
+    {
+        T init = (SR::kAddIsAny && !sr.reads_a() && !sr.reads_b()) ? one_of<T>() : sr.identity();
+        int blocks = (int)std::min<int64_t>((out_len + 255) / 256 + 1, (int64_t)g_num_sms * 16);
+        LAUNCH_NOTE("fill_identity");
+        fill_value_kernel<T><<<blocks, 256, 0, g_stream>>>(t_vals, init, out_len);
+    }
+    if (u_nvals == 0 || arows == 0) return GrB_SUCCESS;
+    int32_t *frontier = dev_alloc_t<int32_t>((size_t)u_nvals);
+    unsigned long long *counter = dev_alloc_t<unsigned long long>(1);
+    if (!frontier || !counter) { dev_free(frontier); dev_free(counter); return set_error(err, GrB_OUT_OF_MEMORY, "frontier"); }
+    CUDA_TRY(err, cudaMemsetAsync(counter, 0, 8, g_stream));
+    {
+        int blocks = (int)std::min<int64_t>((arows + 255) / 256, (int64_t)g_num_sms * 16);
+        LAUNCH_NOTE("compact_frontier");
+        compact_present_kernel<<<blocks, 256, 0, g_stream>>>(up, arows, frontier, counter);
+    }
+    {
+        int blocks = (int)std::min<int64_t>((u_nvals + 7) / 8, (int64_t)g_num_sms * 32);
+        LAUNCH_NOTE("spmspv_push");
+        spmspv_push_kernel<SR, T><<<blocks, 256, 0, g_stream>>>(sr, frontier, u_nvals, A.ptr, A.idx, avals, u, flip, mask, mask_comp, t_vals, t_present);
+    }
+    cudaError_t e = cudaGetLastError();
+    dev_free(frontier); dev_free(counter);
+    CUDA_TRY(err, e);
+    return GrB_SUCCESS;
+}
+
+struct MatVecArgs {
+    GrB_Matrix A; bool use_transpose; GrB_Vector u; bool flip; const uint8_t *mask; bool mask_comp;
+    int add, mul; int64_t out_len; void *t_vals; uint8_t *t_present; std::string *err;
+};
+
+template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
+    GrB_Matrix A = a.A;
+    GrB_Vector u = a.u;
+    GrB_Info info = GrB_SUCCESS;
+    GRB_TRY(vector_count(u));
+    // decide the traversal: rows of M are directly available (pull) unless M = A' and no CSC twin is wanted
+    bool push = false;
+    if (a.use_transpose) {
+        const char *method = opt_get("vxm_method", "auto");
+        if (!strcmp(method, "push")) push = true;
+        else if (!strcmp(method, "pull")) push = false;
+        else {
+            long ratio = opt_get_int("push_ratio", 16);
+            push = u->nvals * ratio <= A->nrows;
+        }
+        if (!push) GRB_TRY(matrix_ensure_twin(A));
+    }
+    CsrArrays &M = (a.use_transpose && !push) ? A->twin : A->csr;
+    const int64_t mrows = (a.use_transpose && !push) ? A->ncols : A->nrows;
+    const int T_code = type_code_of<T>();
+    GRB_DISPATCH_SEMIRING(a.add, a.mul, T, SRT, sr, {
+        const void *av = nullptr, *uv = nullptr;
+        void *atmp = nullptr, *utmp = nullptr;
+        if (sr.reads_a()) info = cast_view(&av, &atmp, M.val, A->type, T_code, A->nvals, a.err);
+        if (!info && sr.reads_b()) info = cast_view(&uv, &utmp, u->vals, u->type, T_code, u->n, a.err);
+        if (!info) {
+            const uint8_t *up = (u->nvals == u->n) ? nullptr : u->present;
+            if (push)
+                info = run_push<SRT, T>(sr, A->csr, A->nrows, a.out_len, (const T *)av, (const T *)uv, u->present,
+                                        u->nvals, a.flip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
+            else
+                info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, up, a.flip, a.mask,
+                                        a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
+        }
+        dev_free(atmp);
+        dev_free(utmp);
+    });
+    return info;
+}
+
+// mask_eff: byte array (1 = mask entry counts) or nullptr; see api.cu for how value masks are reduced to bytes
+GrB_Info multiply_mat_vec_impl(void **t_vals_out, uint8_t **t_present_out, int64_t *t_len, const GrB_Semiring op,
+                               GrB_Matrix A, bool use_transpose, GrB_Vector u, bool flip, const uint8_t *mask_eff,
+                               bool mask_comp, std::string *err) {
+    const int64_t out_len = use_transpose ? A->ncols : A->nrows;
+    const int64_t in_len = use_transpose ? A->nrows : A->ncols;
+    if (u->n != in_len)
+        return set_error(err, GrB_DIMENSION_MISMATCH, "matrix-vector multiply: matrix is %lldx%lld%s, vector has size %lld",
+                         (long long)A->nrows, (long long)A->ncols, use_transpose ? " (transposed)" : "", (long long)u->n);
+    GRB_TRY(matrix_materialize(A));
+    GRB_TRY(vector_ensure_arrays(u));
+    const int D = op->type;
+    size_t n = (size_t)(out_len > 0 ? out_len : 1);
+    void *tv = dev_alloc(n * type_size(D));
+    uint8_t *tp = (uint8_t *)dev_alloc(n);
+    if (!tv || !tp) { dev_free(tv); dev_free(tp); return set_error(err, GrB_OUT_OF_MEMORY, "result vector"); }
+    MatVecArgs a{A, use_transpose, u, flip, mask_eff, mask_comp, op->add, op->mul, out_len, tv, tp, err};
+    GrB_Info info = GrB_NOT_IMPLEMENTED;
+    GRB_DISPATCH_TYPE(D, T, info = mat_vec_typed<T>(a));
+    if (info) { dev_free(tv); dev_free(tp); return info; }
+    *t_vals_out = tv;
+    *t_present_out = tp;
+    *t_len = out_len;
+    return GrB_SUCCESS;
+}

@@ -1,0 +1,190 @@
+"""Device-side extensions of the grb_cuda backend (the analogue of the reference's ``A.ss`` / ``gb.ss``
+namespace: graphblas/core/ss/matrix.py, graphblas/ss/_core.py): device-pointer import/export, stream
+binding, timers, options, kernel accounting.  torch is used only as a device-memory / stream carrier."""
+import ctypes
+
+import numpy as np
+
+from ._lib import GrB_Index, lib
+from .base import call
+from .dtypes import lookup_dtype
+
+
+def set_option(key, value):
+    lib().GrB_cuda_set_option(str(key).encode(), None if value is None else str(value).encode())
+
+
+def get_option(key):
+    return (lib().GrB_cuda_get_option(str(key).encode()) or b"").decode()
+
+
+def sync():
+    call("GrB_cuda_sync", [])
+
+
+def launch_count():
+    return int(lib().GrB_cuda_launch_count())
+
+
+def memory_in_use():
+    return int(lib().GrB_cuda_memory_in_use())
+
+
+def use_torch_stream():
+    """Bind the library to torch's current CUDA stream so torch events / NCCL order with our kernels."""
+    import torch
+
+    call("GrB_cuda_set_stream", [ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)])
+
+
+def timer_start():
+    call("GrB_cuda_timer_start", [])
+
+
+def timer_stop():
+    ms = ctypes.c_float()
+    call("GrB_cuda_timer_stop", [ctypes.byref(ms)])
+    return ms.value
+
+
+def kernel_times(reset=False):
+    L = lib()
+    need = L.GrB_cuda_kernel_names(None, ctypes.c_size_t(0))
+    buf = ctypes.create_string_buffer(max(int(need), 1))
+    L.GrB_cuda_kernel_names(buf, ctypes.c_size_t(need))
+    out = {}
+    for name in [s for s in buf.raw[:need].split(b"\0") if s]:
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        L.GrB_cuda_kernel_time(name, ctypes.byref(ms), ctypes.byref(n))
+        out[name.decode()] = (ms.value, n.value)
+    if reset:
+        L.GrB_cuda_kernel_time(None, None, None)
+    return out
+
+
+def matrix_from_device_csr(indptr, col_indices, values, nrows, ncols, *, sorted=True, name=None):
+    """indptr int64 / col_indices int32 / values: torch CUDA tensors (copied, not adopted)."""
+    from .matrix import Matrix
+
+    dtype = lookup_dtype(str(values.dtype).replace("torch.", "").replace("float32", "FP32").replace("float64", "FP64")
+                         if not str(values.dtype).startswith("torch.") else _torch_dtype(values.dtype))
+    assert indptr.dtype.is_floating_point is False and indptr.element_size() == 8
+    assert col_indices.element_size() == 4
+    h = ctypes.c_void_p()
+    out = Matrix._from_handle(h, dtype, nrows, ncols, name)
+    call("GrB_cuda_Matrix_import_csr32",
+         [ctypes.byref(h), dtype, GrB_Index(nrows), GrB_Index(ncols), ctypes.c_void_p(indptr.data_ptr()),
+          ctypes.c_void_p(col_indices.data_ptr()), ctypes.c_void_p(values.data_ptr()), GrB_Index(col_indices.numel()),
+          1, 1 if sorted else 0])
+    return out
+
+
+def matrix_from_host_csr32(indptr, col_indices, values, nrows, ncols, *, sorted=True, name=None):
+    """host numpy arrays (int64 / int32 / typed; ideally pinned) -> device matrix, no uint64 widening."""
+    from .matrix import Matrix
+
+    dtype = lookup_dtype(values.dtype)
+    h = ctypes.c_void_p()
+    out = Matrix._from_handle(h, dtype, nrows, ncols, name)
+    call("GrB_cuda_Matrix_import_csr32",
+         [ctypes.byref(h), dtype, GrB_Index(nrows), GrB_Index(ncols), ctypes.c_void_p(indptr.ctypes.data),
+          ctypes.c_void_p(col_indices.ctypes.data), ctypes.c_void_p(values.ctypes.data), GrB_Index(col_indices.shape[0]),
+          0, 1 if sorted else 0])
+    return out
+
+
+def matrix_export_host_csr32(A, indptr, col_indices, values, *, sort=False):
+    call("GrB_cuda_Matrix_export_csr32",
+         [ctypes.c_void_p(indptr.ctypes.data) if indptr is not None else None,
+          ctypes.c_void_p(col_indices.ctypes.data) if col_indices is not None else None,
+          ctypes.c_void_p(values.ctypes.data) if values is not None else None,
+          GrB_Index(col_indices.shape[0] if col_indices is not None else A.nvals), A, 1 if sort else 0])
+
+
+def _torch_dtype(dt):
+    import torch
+
+    return {torch.bool: "BOOL", torch.int8: "INT8", torch.int16: "INT16", torch.int32: "INT32", torch.int64: "INT64",
+            torch.uint8: "UINT8", torch.float32: "FP32", torch.float64: "FP64"}[dt]
+
+
+def _np_to_torch_dtype(np_dtype):
+    import torch
+
+    return {"bool": torch.bool, "int8": torch.int8, "int16": torch.int16, "int32": torch.int32, "int64": torch.int64,
+            "uint8": torch.uint8, "uint16": torch.int16, "uint32": torch.int32, "uint64": torch.int64,
+            "float32": torch.float32, "float64": torch.float64}[np.dtype(np_dtype).name]
+
+
+def vector_from_torch(values, present=None, *, name=None):
+    """dense torch CUDA tensor (+ optional uint8 presence) -> Vector (copied)."""
+    from .vector import Vector
+
+    dtype = lookup_dtype(_torch_dtype(values.dtype))
+    h = ctypes.c_void_p()
+    out = Vector._from_handle(h, dtype, values.numel(), name)
+    call("GrB_cuda_Vector_import_dense",
+         [ctypes.byref(h), dtype, GrB_Index(values.numel()), ctypes.c_void_p(values.data_ptr()),
+          None if present is None else ctypes.c_void_p(present.data_ptr()), 1])
+    return out
+
+
+def vector_from_numpy(values, present=None, *, name=None):
+    from .vector import Vector
+
+    values = np.ascontiguousarray(values)
+    dtype = lookup_dtype(values.dtype)
+    h = ctypes.c_void_p()
+    out = Vector._from_handle(h, dtype, values.shape[0], name)
+    call("GrB_cuda_Vector_import_dense",
+         [ctypes.byref(h), dtype, GrB_Index(values.shape[0]), ctypes.c_void_p(values.ctypes.data),
+          None if present is None else ctypes.c_void_p(np.ascontiguousarray(present, dtype=np.uint8).ctypes.data), 0])
+    return out
+
+
+def vector_to_numpy(v, values=None, present=None):
+    values = np.empty(v.size, dtype=v.dtype.np_type) if values is None else values
+    present = np.empty(v.size, dtype=np.uint8) if present is None else present
+    call("GrB_cuda_Vector_export_dense", [ctypes.c_void_p(values.ctypes.data), ctypes.c_void_p(present.ctypes.data), v])
+    return values, present
+
+
+def vector_device_pointers(v):
+    vals, pres = ctypes.c_void_p(), ctypes.c_void_p()
+    call("GrB_cuda_Vector_device_arrays", [v, ctypes.byref(vals), ctypes.byref(pres)])
+    return vals.value, pres.value
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def vector_as_torch(v):
+    """zero-copy torch views (values, present) of the vector's device arrays; call vector_touch(v) after writing."""
+    import torch
+
+    pv, pp = vector_device_pointers(v)
+    n = v.size
+    vals = torch.as_tensor(_CudaArray(pv, (n,), np.dtype(v.dtype.np_type).str if v.dtype.name != "BOOL" else "|u1"), device="cuda")
+    pres = torch.as_tensor(_CudaArray(pp, (n,), "|u1"), device="cuda")
+    return vals, pres
+
+
+def vector_touch(v):
+    call("GrB_cuda_Vector_touch", [v])
+
+
+def matrix_sort(A):
+    call("GrB_cuda_Matrix_sort", [A])
+
+
+def matrix_build_transpose(A):
+    call("GrB_cuda_Matrix_build_transpose", [A])
+
+
+def mxm_symbolic(A, B):
+    """(flops, nvals) of A (+).(x) B without forming it."""
+    f, n = GrB_Index(), GrB_Index()
+    call("GrB_cuda_mxm_symbolic", [ctypes.byref(f), ctypes.byref(n), A, B, None])
+    return f.value, n.value

@@ -1,0 +1,364 @@
+"""Matrix, TransposedMatrix, MatrixExpression -- host mirror of reference graphblas/core/matrix.py for the hot path:
+construction (:190-203), from_coo/build (:627-681), from_csr/_from_csx (:992-1068), to_csr/_to_csx (:1601-1645),
+to_coo (:525-594), mxv (:2233-2262), mxm (:2294-2331), TransposedMatrix (:3825-3920), isequal (:373-415)."""
+import ctypes
+
+import numpy as np
+
+from . import operator
+from ._lib import GrB_Index, lib
+from .base import BaseExpression, BaseType, StructuralMask, ValueMask, call
+from .dtypes import BOOL, FP64, INT64, lookup_dtype, unify
+from .exceptions import NoValue
+from .scalar import Scalar, ScalarExpression
+from .vector import Vector, VectorExpression, _ptr, _Ref, ints_to_numpy_buffer, values_to_numpy_buffer
+
+_name_counter = [0]
+_CSR, _CSC, _COO = 0, 1, 2
+
+
+class Matrix(BaseType):
+    ndim = 2
+    _is_transposed = False
+
+    def __init__(self, dtype=FP64, nrows=0, ncols=0, *, name=None):
+        self.dtype = lookup_dtype(dtype)
+        self._nrows, self._ncols = int(nrows), int(ncols)
+        self.gb_obj = ctypes.c_void_p()
+        if name is None:
+            _name_counter[0] += 1
+            name = f"M_{_name_counter[0]}"
+        self.name = name
+        call("GrB_Matrix_new", [_Ref(self), self.dtype, GrB_Index(self._nrows), GrB_Index(self._ncols)])
+
+    @classmethod
+    def _from_handle(cls, handle, dtype, nrows, ncols, name=None):
+        self = object.__new__(cls)
+        self.dtype, self._nrows, self._ncols, self.gb_obj = lookup_dtype(dtype), int(nrows), int(ncols), handle
+        _name_counter[0] += 1
+        self.name = name or f"M_{_name_counter[0]}"
+        return self
+
+    def __del__(self):
+        gb_obj = getattr(self, "gb_obj", None)
+        if gb_obj is not None and gb_obj.value and lib is not None:
+            try:
+                lib().GrB_Matrix_free(ctypes.byref(gb_obj))
+            except Exception:
+                pass
+
+    @property
+    def _carg(self):
+        return self.gb_obj
+
+    # ---- metadata
+    @property
+    def nrows(self):
+        return self._nrows
+
+    @property
+    def ncols(self):
+        return self._ncols
+
+    @property
+    def shape(self):
+        return (self._nrows, self._ncols)
+
+    @property
+    def nvals(self):
+        n = GrB_Index()
+        call("GrB_Matrix_nvals", [ctypes.byref(n), self])
+        return n.value
+
+    @property
+    def T(self):
+        return TransposedMatrix(self)
+
+    @property
+    def S(self):
+        return StructuralMask(self)
+
+    @property
+    def V(self):
+        return ValueMask(self)
+
+    def __repr__(self):
+        return f"Matrix({self.name!r}, nvals={self.nvals}, nrows={self._nrows}, ncols={self._ncols}, dtype={self.dtype})"
+
+    # ---- data in / out
+    @classmethod
+    def from_coo(cls, rows, columns, values=1.0, dtype=None, *, nrows=None, ncols=None, dup_op=None, name=None):
+        rows, columns = ints_to_numpy_buffer(rows, "rows"), ints_to_numpy_buffer(columns, "columns")
+        if np.ndim(values) == 0:
+            values = np.full(rows.shape[0], values)
+        values, dtype = values_to_numpy_buffer(values, dtype)
+        if nrows is None:
+            if rows.size == 0:
+                raise ValueError("No row indices provided. Unable to infer nrows.")
+            nrows = int(rows.max()) + 1
+        if ncols is None:
+            if columns.size == 0:
+                raise ValueError("No column indices provided. Unable to infer ncols.")
+            ncols = int(columns.max()) + 1
+        C = cls(dtype, nrows, ncols, name=name)
+        C.build(rows, columns, values, dup_op=dup_op)
+        return C
+
+    def build(self, rows, columns, values, *, dup_op=None, clear=False):
+        rows, columns = ints_to_numpy_buffer(rows, "rows"), ints_to_numpy_buffer(columns, "columns")
+        values, _ = values_to_numpy_buffer(values, self.dtype)
+        n = values.shape[0]
+        if rows.shape[0] != n or columns.shape[0] != n:
+            raise ValueError(f"`rows` and `columns` and `values` lengths must match: {rows.size}, {columns.size}, {n}")
+        if clear:
+            self.clear()
+        if dup_op is not None:
+            dup_op = operator.get_typed_op(dup_op, self.dtype, kind="binary")
+            if dup_op.opclass == "Monoid":
+                dup_op = dup_op.binaryop
+        call(f"GrB_Matrix_build_{self.dtype.name}", [self, _ptr(rows), _ptr(columns), _ptr(values), GrB_Index(n), dup_op])
+
+    @classmethod
+    def _from_csx(cls, fmt, indptr, indices, values, dtype, num, check_num, name):
+        """reference core/matrix.py:992-1068 (vanilla path: GrB_Matrix_import_<T>)"""
+        indptr = ints_to_numpy_buffer(indptr, "indptr")
+        indices = ints_to_numpy_buffer(indices, "indices")
+        if np.ndim(values) == 0:
+            values = np.full(indices.shape[0], values)
+        values, dtype = values_to_numpy_buffer(values, dtype)
+        if num is None:
+            if indices.size > 0:
+                num = int(indices.max()) + 1
+            else:
+                raise ValueError(f"No indices provided. Unable to infer {check_num}.")
+        if fmt == _CSR:
+            nrows, ncols = indptr.size - 1, num
+        else:
+            ncols, nrows = indptr.size - 1, num
+        h = ctypes.c_void_p()
+        out = cls._from_handle(h, dtype, nrows, ncols, name)
+        call(f"GrB_Matrix_import_{dtype.name}",
+             [ctypes.byref(h), dtype, GrB_Index(nrows), GrB_Index(ncols), _ptr(indptr), _ptr(indices), _ptr(values),
+              GrB_Index(indptr.size), GrB_Index(indices.size), GrB_Index(values.shape[0]), fmt])
+        return out
+
+    @classmethod
+    def from_csr(cls, indptr, col_indices, values=1.0, dtype=None, *, ncols=None, name=None):
+        return cls._from_csx(_CSR, indptr, col_indices, values, dtype, ncols, "ncols", name)
+
+    @classmethod
+    def from_csc(cls, indptr, row_indices, values=1.0, dtype=None, *, nrows=None, name=None):
+        return cls._from_csx(_CSC, indptr, row_indices, values, dtype, nrows, "nrows", name)
+
+    def _to_csx(self, fmt, dtype=None):
+        """reference core/matrix.py:1601-1645: exportSize, then export into caller-owned numpy buffers"""
+        a, b, c = GrB_Index(), GrB_Index(), GrB_Index()
+        call("GrB_Matrix_exportSize", [ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), fmt, self])
+        Ap = np.empty(a.value, dtype=np.uint64)
+        Ai = np.empty(b.value, dtype=np.uint64)
+        Ax = np.empty(c.value, dtype=self.dtype.np_type)
+        call(f"GrB_Matrix_export_{self.dtype.name}",
+             [_ptr(Ap), _ptr(Ai), _ptr(Ax), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), fmt, self])
+        if dtype is not None and lookup_dtype(dtype) is not self.dtype:
+            Ax = Ax.astype(lookup_dtype(dtype).np_type)
+        return Ap, Ai, Ax   # rows come back sorted by this backend (the reference sorts in numpy when asked)
+
+    def to_csr(self, dtype=None, *, sort=True):
+        return self._to_csx(_CSR, dtype)
+
+    def to_csc(self, dtype=None, *, sort=True):
+        return self._to_csx(_CSC, dtype)
+
+    def to_coo(self, dtype=None, *, rows=True, columns=True, values=True, sort=True):
+        n = self.nvals
+        I = np.empty(n, dtype=np.uint64)
+        J = np.empty(n, dtype=np.uint64)
+        X = np.empty(n, dtype=self.dtype.np_type)
+        nn = GrB_Index(n)
+        call(f"GrB_Matrix_extractTuples_{self.dtype.name}", [_ptr(I), _ptr(J), _ptr(X), ctypes.byref(nn), self])
+        if dtype is not None and lookup_dtype(dtype) is not self.dtype:
+            X = X.astype(lookup_dtype(dtype).np_type)
+        return (I if rows else None, J if columns else None, X if values else None)
+
+    def dup(self, dtype=None, *, name=None):
+        h = ctypes.c_void_p()
+        call("GrB_Matrix_dup", [ctypes.byref(h), self])
+        out = Matrix._from_handle(h, self.dtype, self._nrows, self._ncols, name)
+        if dtype is not None and lookup_dtype(dtype) is not self.dtype:
+            r, c, v = out.to_coo()
+            return Matrix.from_coo(r, c, v.astype(lookup_dtype(dtype).np_type), nrows=self._nrows, ncols=self._ncols, name=name)
+        return out
+
+    def clear(self):
+        call("GrB_Matrix_clear", [self])
+
+    def wait(self, how="materialize"):
+        call("GrB_Matrix_wait", [self, 1 if how == "materialize" else 0])
+        return self
+
+    def __getitem__(self, ij):
+        if isinstance(ij, tuple) and len(ij) == 2 and all(isinstance(k, (int, np.integer)) for k in ij):
+            def thunk():
+                x = self.dtype.ctype()
+                rv = call(f"GrB_Matrix_extractElement_{self.dtype.name}",
+                          [ctypes.byref(x), self, GrB_Index(int(ij[0])), GrB_Index(int(ij[1]))])
+                return None if rv is NoValue else x.value
+            return ScalarExpression(self.dtype, thunk)
+        raise NotImplementedError("only scalar extraction A[i, j] is on this backend's path")
+
+    # ---- expressions
+    def _dup_expr(self):
+        me = self
+
+        def run(out, mask, accum, desc):
+            if mask is not None or accum is not None:
+                raise NotImplementedError("masked / accumulated matrix assignment is outside this backend's path")
+            r, c, v = me.to_coo()
+            out.clear()
+            out.build(r, c, v)
+
+        return MatrixExpression("assign", None, [], dtype=self.dtype, nrows=self._nrows, ncols=self._ncols, custom=run)
+
+    def _scalar_assign_expr(self, value):
+        raise NotImplementedError("scalar assignment into a Matrix is outside this backend's path")
+
+    def mxv(self, other, op=None):
+        """reference core/matrix.py:2233-2262"""
+        return _mxv(self, other, op)
+
+    def mxm(self, other, op=None):
+        """reference core/matrix.py:2294-2331"""
+        return _mxm(self, other, op)
+
+    # ---- comparison (reference core/matrix.py:373-461); done on exported tuples
+    def isequal(self, other, *, check_dtype=False):
+        if type(other) is not Matrix:
+            raise TypeError(f"isequal expects a Matrix, got {type(other).__name__}")
+        if check_dtype and self.dtype != other.dtype:
+            return False
+        if self.shape != other.shape or self.nvals != other.nvals:
+            return False
+        a, b = self.to_coo(), other.to_coo()
+        common = unify(self.dtype, other.dtype).np_type
+        return bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].astype(common), b[2].astype(common)))
+
+    def isclose(self, other, *, rel_tol=1e-7, abs_tol=0.0, check_dtype=False):
+        if check_dtype and self.dtype != other.dtype:
+            return False
+        if self.shape != other.shape or self.nvals != other.nvals:
+            return False
+        a, b = self.to_coo(), other.to_coo()
+        return bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and
+                    np.all(np.isclose(a[2].astype(np.float64), b[2].astype(np.float64), rtol=rel_tol, atol=abs_tol)))
+
+
+class TransposedMatrix:
+    """A.T: the transpose lives only in the descriptor (reference core/matrix.py:3825-3920, _carg :3886-3888)."""
+
+    ndim = 2
+    _is_transposed = True
+
+    def __init__(self, matrix):
+        self._matrix = matrix
+
+    @property
+    def dtype(self):
+        return self._matrix.dtype
+
+    @property
+    def _carg(self):
+        return self._matrix.gb_obj
+
+    @property
+    def name(self):
+        return f"{self._matrix.name}.T"
+
+    @property
+    def gb_name(self):
+        return self._matrix.name
+
+    @property
+    def _nrows(self):
+        return self._matrix._ncols
+
+    @property
+    def _ncols(self):
+        return self._matrix._nrows
+
+    nrows, ncols = _nrows, _ncols
+
+    @property
+    def shape(self):
+        return (self._nrows, self._ncols)
+
+    @property
+    def T(self):
+        return self._matrix
+
+    def mxv(self, other, op=None):
+        return _mxv(self, other, op)
+
+    def mxm(self, other, op=None):
+        return _mxm(self, other, op)
+
+    def __matmul__(self, other):
+        from .infix import matmul
+
+        return matmul(self, other)
+
+    def _transpose_expr(self):
+        me = self._matrix
+
+        def run(out, mask, accum, desc):
+            if mask is not None or accum is not None:
+                raise NotImplementedError("masked transpose is outside this backend's path")
+            Ap, Ai, Ax = me.to_csc()     # CSC of A is CSR of A'
+            new = Matrix.from_csr(Ap, Ai, Ax, me.dtype, ncols=me._nrows)
+            r, c, v = new.to_coo()
+            out.clear()
+            out.build(r, c, v)
+
+        return MatrixExpression("transpose", None, [], dtype=me.dtype, nrows=me._ncols, ncols=me._nrows, custom=run)
+
+    def new(self, dtype=None, *, name=None):
+        out = Matrix(dtype or self.dtype, self._nrows, self._ncols, name=name)
+        out << self
+        return out
+
+
+def _mxv(self, other, op):
+    if not isinstance(other, Vector):
+        raise TypeError(f"mxv expects a Vector, got {type(other).__name__}")
+    op = operator.semiring.plus_times if op is None else op
+    op = operator.get_typed_op(op, self.dtype, other.dtype, kind="semiring")
+    if op.opclass != "Semiring":
+        raise TypeError(f"mxv expects a Semiring, got {op.opclass}")
+    expr = VectorExpression("mxv", "GrB_mxv", [self, other], op=op, size=self._nrows, at=self._is_transposed)
+    if self._ncols != other._size:
+        expr.new(name="")  # incompatible shape; raise now
+    return expr
+
+
+def _mxm(self, other, op):
+    if not isinstance(other, (Matrix, TransposedMatrix)):
+        raise TypeError(f"mxm expects a Matrix, got {type(other).__name__}")
+    op = operator.semiring.plus_times if op is None else op
+    op = operator.get_typed_op(op, self.dtype, other.dtype, kind="semiring")
+    if op.opclass != "Semiring":
+        raise TypeError(f"mxm expects a Semiring, got {op.opclass}")
+    expr = MatrixExpression("mxm", "GrB_mxm", [self, other], op=op, nrows=self._nrows, ncols=other._ncols,
+                            at=self._is_transposed, bt=other._is_transposed)
+    if self._ncols != other._nrows:
+        expr.new(name="")  # incompatible shape; raise now
+    return expr
+
+
+class MatrixExpression(BaseExpression):
+    output_type = Matrix
+
+    def __init__(self, *args, nrows, ncols, **kw):
+        super().__init__(*args, **kw)
+        self._nrows, self._ncols = nrows, ncols
+
+    def construct_output(self, dtype=None, *, name=None):
+        return Matrix(dtype or self.dtype, self._nrows, self._ncols, name=name or None)

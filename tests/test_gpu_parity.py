@@ -1,0 +1,468 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI via the host
+mirror, against (1) the reference's golden vectors, (2) the oracle on seeded random inputs, for every
+traversal (merge-path pull, warp-per-row pull, push) and the hash SpGEMM bins.
+Integer / boolean results and all index patterns are compared bit-exactly; floating point uses inputs whose
+sums are exact (small integers) so those are bit-exact too, plus one tolerance test (rtol stated there)."""
+import numpy as np
+import pytest
+
+import golden_cases as G
+import helpers as H
+from oracle import bigref as R
+from oracle import semantics as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import graphblas_b200 as gb
+
+    gb.init()
+    return gb
+
+
+def _obj(gb, ref):
+    d = G.load(ref)
+    if d["kind"] == "Matrix":
+        return gb.Matrix.from_coo(d["rows"], d["cols"], d["vals"], nrows=d["nrows"], ncols=d["ncols"])
+    return gb.Vector.from_coo(d["idx"], d["vals"], size=d["size"])
+
+
+def _mask(gb, c):
+    if not c["mask"]:
+        return None
+    m = _obj(gb, c["mask"])
+    m = m.S if c["mask_kind"] == "S" else m.V
+    return ~m if c["complement"] else m
+
+
+def _expected(gb, ref):
+    return _obj(gb, ref)
+
+
+def _run_case(gb, c):
+    a, b = _obj(gb, c["a"]), _obj(gb, c["b"])
+    sr = getattr(gb.semiring, c["semiring"])
+    if c["kind"] == "mxm":
+        expr = (a.T if c["ta"] else a).mxm(b.T if c["tb"] else b, sr)
+    elif c["kind"] == "mxv":
+        expr = (a.T if c["ta"] else a).mxv(b, sr)
+    else:
+        expr = a.vxm(b.T if c["tb"] else b, sr)
+    mask = _mask(gb, c)
+    if c["out"] is None:
+        return expr.new(mask=mask) if mask is not None else expr.new()
+    out = _obj(gb, c["out"])
+    kwargs = {}
+    if mask is not None:
+        kwargs["mask"] = mask
+    if c["accum"]:
+        kwargs["accum"] = getattr(gb.binary, c["accum"])
+    if c["replace"]:
+        kwargs["replace"] = True
+    out(**kwargs) << expr
+    return out
+
+
+@pytest.mark.parametrize("method", ["auto", "merge", "rowwarp"])
+@pytest.mark.parametrize("vxm_method", ["auto", "push", "pull"])
+@pytest.mark.parametrize("c", G.CASES, ids=[c["id"] for c in G.CASES])
+def test_reference_goldens(gb, c, method, vxm_method):
+    if c["kind"] == "mxm" and (method != "auto" or vxm_method != "auto"):
+        pytest.skip("spmv options do not affect mxm")
+    gb.cuda.set_option("spmv", method)
+    gb.cuda.set_option("vxm_method", vxm_method)
+    try:
+        got, want = _run_case(gb, c), _expected(gb, c["expect"])
+        assert got.isequal(want), (got.to_coo(), want.to_coo())
+    finally:
+        gb.cuda.set_option("spmv", "auto")
+        gb.cuda.set_option("vxm_method", "auto")
+
+
+def test_nonsquare_max_plus(gb):
+    # reference graphblas/tests/test_matrix.py:335-345
+    a, b = _obj(gb, G.NONSQUARE["a"]), _obj(gb, G.NONSQUARE["b"])
+    C = gb.Matrix(a.dtype, nrows=1, ncols=1)
+    C << a.mxm(b, gb.semiring.max_plus)
+    assert C[0, 0].new() == 33
+    C1 = a.mxm(b, gb.semiring.max_plus).new()
+    assert C1.isequal(C)
+    C2 = a.T.mxm(b.T, gb.semiring.max_plus).new()
+    assert (C2.nrows, C2.ncols) == (5, 5)
+
+
+def test_dimension_mismatch_raises_now(gb):
+    # reference tests/test_matrix.py:1918-1925, tests/test_vector.py:1129-1139
+    A = gb.Matrix.from_coo([0, 1], [0, 1], [1, 2], nrows=2, ncols=3)
+    v = gb.Vector.from_coo([0], [1], size=2)
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        A.mxv(v)
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        A.mxm(A)
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        gb.Vector.from_coo([0], [1], size=5).vxm(A)
+
+
+def test_mask_type_error_and_bad_option(gb):
+    A = _obj(gb, G.A_M)
+    struct_mask = gb.Matrix.from_coo([0, 3, 4], [2, 3, 2], [1, 0, 0], nrows=7, ncols=7)
+    with pytest.raises(TypeError, match="Mask must be"):
+        A.mxm(A).new(mask=struct_mask)     # reference tests/test_matrix.py:373-374
+    with pytest.raises(ValueError, match="Extra descriptor options"):
+        A.mxm(A).new(nthreads=4)           # reference tests/test_matrix.py:4329-4331 (non-suitesparse backend)
+
+
+def test_recorder_call_text(gb):
+    # reference tests/test_recorder.py:31-37 pins the shape of the C call
+    A = gb.Matrix.from_coo([0, 1], [0, 1], [1, 2], nrows=2, ncols=2, name="A")
+    B = gb.Matrix.from_coo([0, 1], [1, 0], [3, 4], nrows=2, ncols=2, name="B")
+    with gb.Recorder() as rec:
+        C = A.mxm(B, gb.semiring.plus_times).new(name="C")
+        D = A.mxm(B.T, gb.semiring.min_plus).new(name="D")
+    assert "GrB_mxm(C, NULL, NULL, GrB_PLUS_TIMES_SEMIRING_INT64, A, B, NULL);" in rec.data
+    assert "GrB_mxm(D, NULL, NULL, GrB_MIN_PLUS_SEMIRING_INT64, A, B.T, GrB_DESC_T1);".replace("B.T", "B") in \
+        [s.replace("B.T", "B") for s in rec.data]
+    assert C.nvals == 2 and D.nvals == 4
+
+
+def test_int64_power_wraps(gb):
+    # reference tests/test_matrix.py:4379-4405 (test_power): chained INT64 mxm wraps, min_plus powers
+    d = G.load(G.A_M)
+    A = _obj(gb, G.A_M)
+    Ab = R.BigMat.from_coo(d["rows"], d["cols"], d["vals"], 7, 7)
+    P, Pb = A.dup(), Ab
+    for i in range(48):
+        P = P.mxm(A, gb.semiring.plus_times).new()
+        Pb = R.mxm_T("plus_times", Pb, Ab)
+        ok, msg = H.mat_equal(P, Pb)
+        assert ok, (i, msg)
+    P, Pb = A.dup(), Ab
+    for i in range(9):
+        P = P.mxm(A, gb.semiring.min_plus).new()
+        Pb = R.mxm_T("min_plus", Pb, Ab)
+        ok, msg = H.mat_equal(P, Pb)
+        assert ok, (i, msg)
+
+
+def test_aliasing(gb):
+    # output aliases inputs and mask: reference tests/test_matrix.py:377-386 and the BFS idiom q(~v.S, replace) << q.vxm(A)
+    rng = np.random.default_rng(5)
+    n = 300
+    r, c = H.random_coo(rng, n, n, 3000)
+    vals = H.random_values(rng, r.size, np.int64)
+    A = gb.Matrix.from_coo(r, c, vals, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, vals, n, n)
+    A(gb.binary.plus) << A.mxm(A, gb.semiring.plus_times)
+    want = R.mxm(Ab, None, "plus", "plus_times", Ab, Ab)
+    ok, msg = H.mat_equal(A, want)
+    assert ok, msg
+    qi = rng.choice(n, 20, replace=False)
+    q = gb.Vector.from_coo(qi, np.ones(20, dtype=bool), size=n)
+    qb = R.BigVec.from_coo(qi, np.ones(20, dtype=bool), n)
+    A2 = gb.Matrix.from_coo(r, c, vals, nrows=n, ncols=n)
+    q(~q.S, replace=True) << q.vxm(A2, gb.semiring.any_pair)
+    want = R.vxm(qb, qb, None, "any_pair", qb, Ab, complement=True, structure=True, replace=True)
+    ok, msg = H.vec_equal(q, want)
+    assert ok, msg
+
+
+SEMIRINGS = ["plus_times", "min_plus", "any_pair", "plus_second", "plus_first", "lor_land", "max_plus", "plus_plus",
+             "min_first", "max_times", "min_second", "plus_pair", "plus_min"]
+DTYPES = [np.int64, np.int32, np.int8, np.uint16, np.uint64, np.float32, np.float64, np.bool_]
+
+
+def _semiring_ok(semiring, dtype):
+    if dtype == np.bool_:
+        return semiring in ("lor_land", "any_pair")
+    return True
+
+
+@pytest.mark.parametrize("semiring", SEMIRINGS)
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_vector_multiplies_vs_oracle(gb, semiring, dtype):
+    """mxv / mxv(A.T) / vxm / vxm(A.T) x (merge, rowwarp, push, pull) x masks x accum on random rectangular input."""
+    if not _semiring_ok(semiring, dtype):
+        pytest.skip("semiring/dtype combination not defined")
+    rng = np.random.default_rng(abs(hash((semiring, np.dtype(dtype).name))) % 2**32)
+    nr, nc = 700, 450
+    r, c = H.random_coo(rng, nr, nc, 9000)
+    av = H.random_values(rng, r.size, dtype)
+    A = gb.Matrix.from_coo(r, c, av, nrows=nr, ncols=nc)
+    Ab = R.BigMat.from_coo(r, c, av, nr, nc)
+    sr = getattr(gb.semiring, semiring)
+    accum_name = "lor" if dtype == np.bool_ else "min"
+    for trial in range(3):
+        dens_u = [0.9, 0.05, 1.0][trial]
+        for kind in ("mxv", "mxv_T", "vxm", "vxm_T"):
+            in_len = nc if kind in ("mxv", "vxm_T") else nr
+            out_len = nr if kind in ("mxv", "vxm_T") else nc
+            ui = np.flatnonzero(rng.random(in_len) < dens_u)
+            uv = H.random_values(rng, ui.size, dtype)
+            wi = np.flatnonzero(rng.random(out_len) < 0.5)
+            wv = H.random_values(rng, wi.size, dtype)
+            mi = np.flatnonzero(rng.random(out_len) < 0.5)
+            mv = rng.integers(0, 2, mi.size).astype(np.int8)
+            for (use_mask, comp, struct, repl, accum) in [(False, False, False, False, None), (True, False, True, False, None),
+                                                          (True, True, True, True, None), (True, False, False, True, accum_name),
+                                                          (True, True, False, False, accum_name), (False, False, False, False, accum_name)]:
+                for method, vxm_method in [("merge", "pull"), ("rowwarp", "push"), ("auto", "auto")]:
+                    gb.cuda.set_option("spmv", method)
+                    gb.cuda.set_option("vxm_method", vxm_method)
+                    u = H.gb_vector(gb, ui, uv, in_len)
+                    w = H.gb_vector(gb, wi, wv, out_len)
+                    kwargs = {}
+                    if use_mask:
+                        m = H.gb_vector(gb, mi, mv, out_len)
+                        mk = m.S if struct else m.V
+                        kwargs["mask"] = ~mk if comp else mk
+                    if accum:
+                        kwargs["accum"] = getattr(gb.binary, accum)
+                    if repl:
+                        kwargs["replace"] = True
+                    expr = {"mxv": lambda: A.mxv(u, sr), "mxv_T": lambda: A.T.mxv(u, sr), "vxm": lambda: u.vxm(A, sr),
+                            "vxm_T": lambda: u.vxm(A.T, sr)}[kind]()
+                    w(**kwargs) << expr
+                    ub = R.BigVec.from_coo(ui, uv, in_len, dtype=dtype)
+                    wb = R.BigVec.from_coo(wi, wv, out_len, dtype=dtype)
+                    mb = R.BigVec.from_coo(mi, mv, out_len, dtype=np.int8) if use_mask else None
+                    okw = dict(complement=comp, structure=struct, replace=repl)
+                    if kind == "mxv":
+                        want = R.mxv(wb, mb, accum, semiring, Ab, ub, **okw)
+                    elif kind == "mxv_T":
+                        want = R.mxv(wb, mb, accum, semiring, Ab, ub, t0=True, **okw)
+                    elif kind == "vxm":
+                        want = R.vxm(wb, mb, accum, semiring, ub, Ab, **okw)
+                    else:
+                        want = R.vxm(wb, mb, accum, semiring, ub, Ab, t1=True, **okw)
+                    ok, msg = H.vec_equal(w, want)
+                    assert ok, (semiring, dtype, kind, trial, use_mask, comp, struct, repl, accum, method, vxm_method, msg)
+    gb.cuda.set_option("spmv", "auto")
+    gb.cuda.set_option("vxm_method", "auto")
+
+
+@pytest.mark.parametrize("semiring", ["plus_times", "min_plus", "any_pair", "plus_second", "lor_land", "max_plus", "plus_pair"])
+@pytest.mark.parametrize("dtype", [np.int64, np.int16, np.float32, np.float64, np.bool_], ids=lambda d: np.dtype(d).name)
+def test_mxm_vs_oracle(gb, semiring, dtype):
+    if not _semiring_ok(semiring, dtype):
+        pytest.skip("semiring/dtype combination not defined")
+    rng = np.random.default_rng(abs(hash(("mxm", semiring, np.dtype(dtype).name))) % 2**32)
+    m, k, n = 260, 310, 240
+    ar, ac = H.random_coo(rng, m, k, 5000)
+    br, bc = H.random_coo(rng, k, n, 6000)
+    av, bv = H.random_values(rng, ar.size, dtype), H.random_values(rng, br.size, dtype)
+    A, B = gb.Matrix.from_coo(ar, ac, av, nrows=m, ncols=k), gb.Matrix.from_coo(br, bc, bv, nrows=k, ncols=n)
+    Ab, Bb = R.BigMat.from_coo(ar, ac, av, m, k), R.BigMat.from_coo(br, bc, bv, k, n)
+    sr = getattr(gb.semiring, semiring)
+    C = A.mxm(B, sr).new()
+    ok, msg = H.mat_equal(C, R.mxm_T(semiring, Ab, Bb))
+    assert ok, msg
+    # transposed operands
+    Bt = gb.Matrix.from_coo(bc, br, bv, nrows=n, ncols=k)
+    ok, msg = H.mat_equal(A.mxm(Bt.T, sr).new(), R.mxm_T(semiring, Ab, Bb))
+    assert ok, "T1 " + msg
+    At = gb.Matrix.from_coo(ac, ar, av, nrows=k, ncols=m)
+    ok, msg = H.mat_equal(At.T.mxm(B, sr).new(), R.mxm_T(semiring, Ab, Bb))
+    assert ok, "T0 " + msg
+    # mask / accum / replace
+    cr, cc = H.random_coo(rng, m, n, 4000)
+    cv = H.random_values(rng, cr.size, dtype)
+    mr, mc = H.random_coo(rng, m, n, 20000)
+    mv = rng.integers(0, 2, mr.size).astype(np.int8)
+    accum_name = "lor" if dtype == np.bool_ else "plus"
+    for (use_mask, comp, struct, repl, accum) in [(True, False, True, False, None), (True, True, False, True, None),
+                                                  (True, False, False, True, accum_name), (False, False, False, False, accum_name),
+                                                  (True, True, True, False, accum_name)]:
+        Cg = gb.Matrix.from_coo(cr, cc, cv, nrows=m, ncols=n)
+        kwargs = {}
+        if use_mask:
+            Mg = gb.Matrix.from_coo(mr, mc, mv, nrows=m, ncols=n)
+            mk = Mg.S if struct else Mg.V
+            kwargs["mask"] = ~mk if comp else mk
+        if accum:
+            kwargs["accum"] = getattr(gb.binary, accum)
+        if repl:
+            kwargs["replace"] = True
+        Cg(**kwargs) << A.mxm(B, sr)
+        want = R.mxm(R.BigMat.from_coo(cr, cc, cv, m, n), R.BigMat.from_coo(mr, mc, mv, m, n) if use_mask else None,
+                     accum, semiring, Ab, Bb, complement=comp, structure=struct, replace=repl)
+        ok, msg = H.mat_equal(Cg, want)
+        assert ok, (use_mask, comp, struct, repl, accum, msg)
+
+
+def test_mxm_all_bins(gb):
+    """Rows whose flop counts span every SpGEMM bin, including the global-hash-table bin (>8192 products/row)."""
+    rng = np.random.default_rng(11)
+    n = 6000
+    rows, cols = [], []
+    # row i gets degree deg[i]; B = A, and a few dense-ish columns' rows make the products explode
+    deg = np.concatenate([np.zeros(500, int), rng.integers(1, 4, 3000), rng.integers(4, 40, 2000), rng.integers(40, 400, 480),
+                          np.full(20, 2500)])
+    rng.shuffle(deg)
+    for i, d in enumerate(deg):
+        if d:
+            cs = rng.choice(n, size=d, replace=False)
+            rows.append(np.full(d, i))
+            cols.append(cs)
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    v = rng.integers(-3, 4, r.size).astype(np.int64)
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    flops, nvals = gb.cuda.mxm_symbolic(A, A)
+    T = R.mxm_T("plus_times", Ab, Ab)
+    assert nvals == T.nvals
+    deg_b = np.diff(Ab.indptr)
+    assert flops == int(deg_b[Ab.indices].sum())
+    C = A.mxm(A, gb.semiring.plus_times).new()
+    ok, msg = H.mat_equal(C, T)
+    assert ok, msg
+    C2 = A.mxm(A, gb.semiring.min_plus).new()
+    ok, msg = H.mat_equal(C2, R.mxm_T("min_plus", Ab, Ab))
+    assert ok, msg
+    Cf = gb.Matrix.from_coo(r, c, v.astype(np.float64), nrows=n, ncols=n)
+    C3 = Cf.mxm(Cf, gb.semiring.plus_times).new()
+    ok, msg = H.mat_equal(C3, R.mxm_T("plus_times", R.BigMat.from_coo(r, c, v.astype(np.float64), n, n), R.BigMat.from_coo(r, c, v.astype(np.float64), n, n)))
+    assert ok, msg
+
+
+@pytest.mark.parametrize("scale", [10, 14])
+def test_rmat_parity(gb, scale):
+    """R-MAT (Graph500 parameters): skewed degrees exercise merge-path carries across tiles and heavy SpGEMM rows."""
+    r, c, n = H.rmat_edges(scale, seed=42)
+    rng = np.random.default_rng(1)
+    w = rng.integers(1, 256, r.size).astype(np.int64)
+    A = gb.Matrix.from_coo(r, c, w, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, w, n, n)
+    x = rng.integers(0, 1000, n).astype(np.int64)
+    v = gb.Vector.from_coo(np.arange(n), x, size=n)
+    vb = R.BigVec(x, np.ones(n, np.uint8))
+    for method in ("merge", "rowwarp"):
+        gb.cuda.set_option("spmv", method)
+        for sr in ("min_plus", "plus_times", "plus_second", "any_pair"):
+            ok, msg = H.vec_equal(A.mxv(v, getattr(gb.semiring, sr)).new(), R.mxv_T(sr, Ab, vb))
+            assert ok, (method, sr, msg)
+            gb.cuda.set_option("vxm_method", "pull")
+            ok, msg = H.vec_equal(v.vxm(A, getattr(gb.semiring, sr)).new(), R.vxm_push_T(sr, vb, Ab))
+            assert ok, (method, "vxm", sr, msg)
+            gb.cuda.set_option("vxm_method", "auto")
+    gb.cuda.set_option("spmv", "auto")
+    # fp32 with a stated tolerance: summation order differs (rtol 1e-5 * sqrt(max row products) is the contract; use 1e-4)
+    wf = rng.random(r.size).astype(np.float32)
+    Af = gb.Matrix.from_coo(r, c, wf, nrows=n, ncols=n)
+    xf = rng.random(n).astype(np.float32)
+    got = Af.mxv(gb.Vector.from_coo(np.arange(n), xf, size=n), gb.semiring.plus_times).new()
+    want = R.mxv_T("plus_times", R.BigMat.from_coo(r, c, wf, n, n), R.BigVec(xf, np.ones(n, np.uint8)))
+    ok, msg = H.vec_equal(got, want, rtol=1e-4)
+    assert ok, msg
+    if scale <= 10:
+        C = A.mxm(A, gb.semiring.plus_times).new()
+        ok, msg = H.mat_equal(C, R.mxm_T("plus_times", Ab, Ab))
+        assert ok, msg
+        M = A.mxm(A, gb.semiring.plus_times).new(mask=A.S)
+        want = R.mxm(R.BigMat(np.zeros(n + 1), [], np.zeros(0, np.int64), n, n), Ab, None, "plus_times", Ab, Ab, structure=True)
+        ok, msg = H.mat_equal(M, want)
+        assert ok, msg
+
+
+def test_bfs_sssp_pagerank_loops(gb):
+    """The three iterative workloads of BASELINE.json configs 3-5 as written in the reference notebooks,
+    device-resident, against the same loops run on the oracle."""
+    r, c, n = H.rmat_edges(11, seed=7)
+    rng = np.random.default_rng(3)
+    w = rng.integers(1, 256, r.size).astype(np.int64)
+    A = gb.Matrix.from_coo(r, c, w, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, w, n, n)
+    src = int(r[0])
+    # ---- level BFS: q<~v.S, replace> = q any_pair A
+    q = gb.Vector.from_coo([src], [True], size=n)
+    v = gb.Vector(gb.dtypes.INT64, n)
+    qb = R.BigVec.from_coo([src], [True], n)
+    vb = R.BigVec.empty(n, np.int64)
+    for level in range(1, n):
+        v(mask=q.V)[:] = level
+        vb = R.vec_write_back(vb, R.BigVec(np.full(n, level, np.int64), np.ones(n, np.uint8)), qb, None, False, False, False)
+        q(~v.S, replace=True) << q.vxm(A, gb.semiring.any_pair)
+        qb = R.vxm(qb, vb, None, "any_pair", qb, Ab, complement=True, structure=True, replace=True)
+        ok, msg = H.vec_equal(q, qb)
+        assert ok, (level, msg)
+        if q.nvals == 0:
+            break
+    ok, msg = H.vec_equal(v, vb)
+    assert ok, msg
+    assert v.nvals > n // 8
+    # ---- SSSP (Bellman-Ford): w(min) << w.vxm(A, min_plus) to a fixed point
+    d = gb.Vector.from_coo([src], [0], size=n, dtype=gb.dtypes.INT64)
+    db = R.BigVec.from_coo([src], np.array([0], dtype=np.int64), n)
+    for it in range(n):
+        old = d.dup()
+        d(gb.binary.min) << d.vxm(A, gb.semiring.min_plus)
+        db = R.vxm(db, None, "min", "min_plus", db, Ab)
+        if d.isequal(old):
+            break
+    ok, msg = H.vec_equal(d, db)
+    assert ok, msg
+    # ---- PageRank: r(plus) << A.T.mxv(w, plus_second), 10 fixed iterations, fp64, rtol 1e-10
+    Af = gb.Matrix.from_coo(r, c, np.ones(r.size), nrows=n, ncols=n)
+    Afb = R.BigMat.from_coo(r, c, np.ones(r.size), n, n)
+    deg = np.maximum(np.diff(Afb.indptr), 1).astype(np.float64)
+    dvec = gb.Vector.from_coo(np.arange(n), deg, size=n)
+    t = gb.Vector.from_coo(np.arange(n), np.full(n, 1.0 / n), size=n)
+    tb = np.full(n, 1.0 / n)
+    damping, teleport = 0.85, (1 - 0.85) / n
+    for it in range(10):
+        wv = t.ewise_mult(dvec, gb.binary.truediv if hasattr(gb.binary, "truediv") else gb.binary.cdiv).new()
+        wv = wv.apply(gb.binary.times, right=damping).new()
+        rr = gb.Vector(gb.dtypes.FP64, n)
+        rr[:] = teleport
+        rr(gb.binary.plus) << Af.T.mxv(wv, gb.semiring.plus_second)
+        t = rr
+        wb = damping * tb / deg
+        prod = R.mxv_T("plus_second", Afb.T(), R.BigVec(wb, np.ones(n, np.uint8)))
+        tb = teleport + np.where(prod.present.astype(bool), prod.vals, 0.0)
+    got = t.to_dense(fill_value=0.0)
+    np.testing.assert_allclose(got, tb, rtol=1e-10, atol=0)
+    assert abs(t.reduce(gb.monoid.plus).value - tb.sum()) < 1e-9
+
+
+def test_io_roundtrips(gb):
+    # reference tests/test_matrix.py:3965-4004 (CSR/CSC round trips, malformed input)
+    rng = np.random.default_rng(2)
+    r, c = H.random_coo(rng, 50, 70, 600)
+    v = rng.random(r.size)
+    A = gb.Matrix.from_coo(r, c, v, nrows=50, ncols=70)
+    Ap, Ai, Ax = A.to_csr()
+    B = gb.Matrix.from_csr(Ap, Ai, Ax, ncols=70)
+    assert B.isequal(A)
+    Cp, Ci, Cx = A.to_csc()
+    C = gb.Matrix.from_csc(Cp, Ci, Cx, nrows=50)
+    assert C.isequal(A)
+    import scipy.sparse as sp
+
+    S_ = sp.csr_matrix((v, (r, c)), shape=(50, 70))
+    S_.sort_indices()
+    assert np.array_equal(Ap, S_.indptr) and np.array_equal(Ai, S_.indices) and np.array_equal(Ax, S_.data)
+    Sc = S_.tocsc()
+    Sc.sort_indices()
+    assert np.array_equal(Cp, Sc.indptr) and np.array_equal(Ci, Sc.indices) and np.array_equal(Cx, Sc.data)
+    # unsorted CSR is accepted and sorted lazily
+    perm = np.concatenate([rng.permutation(np.arange(Ap[i], Ap[i + 1])) for i in range(50)]).astype(np.int64)
+    D = gb.Matrix.from_csr(Ap, Ai[perm], Ax[perm], ncols=70)
+    assert D.isequal(A)
+    # duplicates: error without dup_op, reduced with it
+    with pytest.raises(gb.exceptions.InvalidValue):
+        gb.Matrix.from_coo([0, 0], [1, 1], [1, 2], nrows=2, ncols=2)
+    E = gb.Matrix.from_coo([0, 0, 1], [1, 1, 0], [1, 2, 5], nrows=2, ncols=2, dup_op=gb.binary.plus)
+    assert E.to_coo()[2].tolist() == [3, 5]
+    with pytest.raises(gb.exceptions.IndexOutOfBound):
+        gb.Matrix.from_coo([0, 5], [1, 1], [1, 2], nrows=2, ncols=2)
+    with pytest.raises(gb.exceptions.InvalidValue):
+        gb.Matrix.from_csr([0, 3, 2], [0, 1, 0], [1.0, 2.0, 3.0], ncols=2)
+    # vectors, incl. stored explicit zeros (reference fixture v has an explicit 0 at index 6)
+    vv = gb.Vector.from_coo([1, 3, 4, 6], [1, 1, 2, 0])
+    assert vv.nvals == 4 and vv.to_coo()[1].tolist() == [1, 1, 2, 0]
+    # huge vectors cannot be held densely: clean error, not a crash (reference tests/test_vector.py:59-66 uses 2**59)
+    big = gb.Vector(gb.dtypes.INT64, 2**59 + 1)
+    assert big.nvals == 0
+    with pytest.raises((gb.exceptions.OutOfMemory, gb.exceptions.IndexOutOfBound)):
+        big.build([0, 2**59], [0, 1])
