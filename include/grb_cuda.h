@@ -161,6 +161,47 @@ GrB_Info GrB_cuda_Vector_setElement(GrB_Vector w, const void *x, GrB_Type xtype,
 GrB_Info GrB_cuda_Vector_extractElement(void *x, GrB_Type xtype, const GrB_Vector v, GrB_Index i);
 GrB_Info GrB_Vector_removeElement(GrB_Vector w, GrB_Index i);
 
+/* ------------------------------------------------------------------ typed C-API names (one set per builtin type)
+ * These are the exact symbols the reference formats and looks up, e.g. f"GrB_Matrix_import_{dtype.name}"
+ * (graphblas/core/matrix.py:1040-1060), f"GrB_Matrix_export_{dtype_name}" (:1618-1621),
+ * f"GrB_Matrix_build_{dtype_name}" (:660-676), f"GrB_Vector_extractTuples_{dtype_name}" (core/vector.py:500-510). */
+#define GRB_CUDA_DECLARE_TYPED(SFX, CT)                                                                              \
+    GrB_Info GrB_Matrix_import_##SFX(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols,               \
+                                     const GrB_Index *Ap, const GrB_Index *Ai, const CT *Ax, GrB_Index Ap_len,      \
+                                     GrB_Index Ai_len, GrB_Index Ax_len, GrB_Format format);                        \
+    GrB_Info GrB_Matrix_export_##SFX(GrB_Index *Ap, GrB_Index *Ai, CT *Ax, GrB_Index *Ap_len, GrB_Index *Ai_len,    \
+                                     GrB_Index *Ax_len, GrB_Format format, GrB_Matrix A);                           \
+    GrB_Info GrB_Matrix_build_##SFX(GrB_Matrix C, const GrB_Index *I, const GrB_Index *J, const CT *X,              \
+                                    GrB_Index nvals, const GrB_BinaryOp dup);                                       \
+    GrB_Info GrB_Matrix_extractTuples_##SFX(GrB_Index *I, GrB_Index *J, CT *X, GrB_Index *nvals, const GrB_Matrix A); \
+    GrB_Info GrB_Matrix_extractElement_##SFX(CT *x, const GrB_Matrix A, GrB_Index i, GrB_Index j);                  \
+    GrB_Info GrB_Vector_build_##SFX(GrB_Vector w, const GrB_Index *I, const CT *X, GrB_Index nvals,                 \
+                                    const GrB_BinaryOp dup);                                                        \
+    GrB_Info GrB_Vector_extractTuples_##SFX(GrB_Index *I, CT *X, GrB_Index *nvals, const GrB_Vector v);             \
+    GrB_Info GrB_Vector_setElement_##SFX(GrB_Vector w, CT x, GrB_Index i);                                          \
+    GrB_Info GrB_Vector_extractElement_##SFX(CT *x, const GrB_Vector v, GrB_Index i);                               \
+    GrB_Info GrB_Vector_reduce_##SFX(CT *val, const GrB_BinaryOp accum, const GrB_Monoid op, const GrB_Vector u,    \
+                                     const GrB_Descriptor desc);                                                    \
+    GrB_Info GrB_Vector_assign_##SFX(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, CT val,         \
+                                     const GrB_Index *indices, GrB_Index ni, const GrB_Descriptor desc);
+GRB_CUDA_DECLARE_TYPED(BOOL, bool)
+GRB_CUDA_DECLARE_TYPED(INT8, int8_t)
+GRB_CUDA_DECLARE_TYPED(INT16, int16_t)
+GRB_CUDA_DECLARE_TYPED(INT32, int32_t)
+GRB_CUDA_DECLARE_TYPED(INT64, int64_t)
+GRB_CUDA_DECLARE_TYPED(UINT8, uint8_t)
+GRB_CUDA_DECLARE_TYPED(UINT16, uint16_t)
+GRB_CUDA_DECLARE_TYPED(UINT32, uint32_t)
+GRB_CUDA_DECLARE_TYPED(UINT64, uint64_t)
+GRB_CUDA_DECLARE_TYPED(FP32, float)
+GRB_CUDA_DECLARE_TYPED(FP64, double)
+extern const GrB_Index *GrB_ALL;
+/* w<mask> accum= op(scalar, u) (scalar_first != 0) or op(u, scalar): GrB_Vector_apply_BinaryOp1st/2nd_<T> */
+GrB_Info GrB_cuda_Vector_apply_binop(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                     const GrB_Vector u, const void *scalar, GrB_Type scalar_type, int scalar_first,
+                                     const GrB_Descriptor desc);
+size_t GrB_cuda_kernel_names(char *buf, size_t buflen);
+
 /* ------------------------------------------------------------------ device-side extensions (the GxB_ analogue;
  * precedent: graphblas/core/ss/descriptor.py:77-83 axb_method, ss/_core.py:129-138 gpu_id) */
 /* fast import with the device's own index widths (int64 row pointers, int32 column indices); `on_device`

@@ -335,8 +335,8 @@ __global__ void reduce_runs_kernel(const uint64_t *keys, const int64_t *pos, con
         T acc = xin[pos[k]];
         for (int64_t q = k + 1; q < n && keys[q] == keys[k]; q++) acc = binop<T>(dup_op, acc, xin[pos[q]]);
         int64_t o = scan[k];
-        if (out_row) out_row[o] = (int32_t)(keys[k] / ncols);
-        out_col[o] = (int32_t)(keys[k] % ncols);
+        if (out_row) { out_row[o] = (int32_t)(keys[k] / ncols); out_col[o] = (int32_t)(keys[k] % ncols); }
+        else out_col[o] = (int32_t)keys[k];   // vectors: the key is the index itself
         out_val[o] = acc;
     }
 }

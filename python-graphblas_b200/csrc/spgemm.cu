@@ -286,17 +286,22 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 size_t per = (((size_t)table * entry + 8) + 7) & ~(size_t)7;
                 size_t smem = per * rpb;
                 auto kern = spgemm_hash_kernel<SR, T, NUMERIC, true>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
                 kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, table, shift, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Cp, a.Cj, (T *)a.Cx, nullptr, nullptr, nullptr);
             } else {
                 size_t smem = (size_t)table * entry;
                 auto kern = spgemm_hash_kernel<SR, T, NUMERIC, false>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
                 kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, n, table, shift, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Cp, a.Cj, (T *)a.Cx, nullptr, nullptr, nullptr);
             }
-            CUDA_TRY(err, cudaGetLastError());
+            {
+                cudaError_t le = cudaGetLastError();
+                if (le != cudaSuccess)
+                    return set_error(err, GrB_PANIC, "spgemm %s kernel launch failed in bin %d (table %d, %d threads, %lld rows, entry %zu B): %s",
+                                     NUMERIC ? "numeric" : "symbolic", b, table, threads, (long long)n, entry, cudaGetErrorString(le));
+            }
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);

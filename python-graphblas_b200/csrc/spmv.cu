@@ -481,7 +481,21 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
     CsrArrays &M = (a.use_transpose && !push) ? A->twin : A->csr;
     const int64_t mrows = (a.use_transpose && !push) ? A->ncols : A->nrows;
     const int T_code = type_code_of<T>();
-    GRB_DISPATCH_SEMIRING(a.add, a.mul, T, SRT, sr, {
+    // vxm multiplies mul(u_k, a): fold the operand swap into the operator so kernels always compute mul(a, x)
+    int mul = a.mul;
+    if (a.flip) {
+        switch (mul) {
+            case OP_FIRST: mul = OP_SECOND; break;
+            case OP_SECOND: mul = OP_FIRST; break;
+            case OP_MINUS: mul = OP_RMINUS; break;
+            case OP_RMINUS: mul = OP_MINUS; break;
+            case OP_DIV: mul = OP_RDIV; break;
+            case OP_RDIV: mul = OP_DIV; break;
+            default: break;   // commutative multiplies
+        }
+    }
+    const bool kflip = false;
+    GRB_DISPATCH_SEMIRING(a.add, mul, T, SRT, sr, {
         const void *av = nullptr, *uv = nullptr;
         void *atmp = nullptr, *utmp = nullptr;
         if (sr.reads_a()) info = cast_view(&av, &atmp, M.val, A->type, T_code, A->nvals, a.err);
@@ -490,9 +504,9 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             const uint8_t *up = (u->nvals == u->n) ? nullptr : u->present;
             if (push)
                 info = run_push<SRT, T>(sr, A->csr, A->nrows, a.out_len, (const T *)av, (const T *)uv, u->present,
-                                        u->nvals, a.flip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
+                                        u->nvals, kflip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
             else
-                info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, up, a.flip, a.mask,
+                info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, up, kflip, a.mask,
                                         a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
         }
         dev_free(atmp);

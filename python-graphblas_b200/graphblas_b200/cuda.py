@@ -34,7 +34,8 @@ def use_torch_stream():
     """Bind the library to torch's current CUDA stream so torch events / NCCL order with our kernels."""
     import torch
 
-    call("GrB_cuda_set_stream", [ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)])
+    h = torch.cuda.current_stream().cuda_stream
+    call("GrB_cuda_set_stream", [ctypes.c_void_p(h if h else 1)])   # 1 == cudaStreamLegacy (the NULL stream)
 
 
 def timer_start():
