@@ -1,18 +1,23 @@
-// spgemm.cu -- T = A (+).(x) B for GrB_mxm: two-phase, flop-binned hash SpGEMM (row-wise Gustavson).
+// spgemm.cu -- T = A (+).(x) B for GrB_mxm: flop-binned hash SpGEMM (row-wise Gustavson), sm_100a.
 //
-//   1. row_flops : flops(i) = sum_{k in A(i,:)} nnz(B(k,:))                       (upper bound on nnz(T(i,:)))
-//   2. symbolic  : rows binned by flops; per bin a hash-set kernel counts the distinct columns of the row
-//                  (warp-per-row / CTA-per-row with the table in shared memory, global-memory table for the
-//                  few rows whose bound exceeds the largest shared table)
-//   3. scan      : row_nnz -> row pointers of T, exact allocation
-//   4. numeric   : rows re-binned by exact nnz; same kernels with a value array next to the keys, semiring
-//                  multiply + atomic monoid combine in shared memory, then compaction into T (unsorted within
-//                  a row: T is marked "jumbled" and sorted lazily, exactly as the reference's C library
-//                  allows -- graphblas/core/matrix.py:1631-1644)
+//   row_flops : flops(i) = sum_{k in A(i,:)} nnz(B(k,:))   -- upper bound on nnz(T(i,:)); rows are binned by it.
+//   one-pass  (default when 2*flops*(4+s_val) bytes fit): every row is hashed ONCE, writing its entries into a
+//               staging CSR addressed by the flops prefix and recording the exact row count; an exclusive scan and a
+//               streaming compaction produce the final CSR.  No symbolic pass at all.
+//   two-pass  (memory-tight products, e.g. Graph500 skew): symbolic hash-set pass counts nnz per row, exact
+//               allocation, rows re-binned by nnz, numeric pass.
 //
-// Within a row, sub-groups of 8 lanes take one A(i,k) each and stride the B(k,:) row, so B is read with
-// contiguous 32-byte segments.  Table sizes are run-time (dynamic shared memory), so one kernel
-// instantiation per (semiring, type) serves every bin.
+// Hash kernels.  Rows with <= 150 products: one warp per row, table in shared memory.  Larger rows: one CTA per
+// row; the A row is staged in shared memory a chunk at a time together with the start/length of every B row it
+// selects (one round trip per level of indirection for the whole chunk), the chunk's products are cut into work
+// items of 32 consecutive B entries, and 8-lane sub-groups pull items round-robin, issuing all loads of an item
+// before the first insert (no dependent chain per A entry, no straggler on a long B row).  Tables are sized per
+// row (1.6 x count, any size: multiply-shift range reduction instead of a power-of-two mask) inside the bin's
+// shared-memory allocation; rows beyond the largest shared table use global-memory tables.  For value types of
+// <= 4 bytes an entry is ONE 64-bit word (key:value) claimed by a single atomicCAS -- one shared-memory atomic per
+// product instead of two; accumulation into an existing key is an atomic monoid combine on the value half.
+// Rows come out unsorted ("jumbled"); sorting is lazy (structure.cu), as the reference's C library allows
+// (graphblas/core/matrix.py:1631-1644).
 //
 // Serves GrB_mxm: reference graphblas/core/matrix.py:2319-2328 (call assembled at core/base.py:496-503).
 #include <cub/cub.cuh>
@@ -21,9 +26,108 @@
 #include "grb_ops.cuh"
 
 constexpr int HASH_EMPTY = -1;
-constexpr int LPE = 8;   // lanes per A entry
+constexpr unsigned long long HASH_EMPTY64 = ~0ull;
+constexpr int LPE = 8;    // lanes per A entry in the warp-per-row kernel
+constexpr int MAX_THREADS = 512;
 
-__device__ __forceinline__ unsigned hash_slot(int key, int shift) { return ((unsigned)key * 0x9E3779B1u) >> shift; }
+__device__ __forceinline__ unsigned hash_slot(int key, unsigned size) {
+    return (unsigned)(((unsigned long long)((unsigned)key * 0x9E3779B1u) * size) >> 32);   // multiply-shift into [0, size)
+}
+__device__ __forceinline__ int table_size_for(int64_t cnt, int cap, int tf8) {
+    int64_t s = ((cnt * tf8) >> 3) + 8;   // tf8/8 x count
+    if (s < 32) s = 32;
+    return (int)(s > cap ? cap : s);
+}
+template <typename T> struct Packed { static constexpr bool value = sizeof(T) <= 4; };
+template <typename T> __device__ __forceinline__ unsigned long long pack_entry(int key, T v) {
+    unsigned int bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    return ((unsigned long long)(unsigned)key << 32) | bits;
+}
+template <typename T> __device__ __forceinline__ T unpack_value(unsigned long long e) {
+    unsigned int bits = (unsigned int)e;
+    T v;
+    memcpy(&v, &bits, sizeof(T));
+    return v;
+}
+
+// ---- the table: symbolic (keys only), numeric packed (key:value in one 64-bit word), numeric split (keys + values)
+template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
+    static constexpr bool kPacked = NUMERIC && PACK && Packed<T>::value;
+    int *keys;
+    T *vals;
+    unsigned long long *ent;
+    unsigned size;
+    __device__ __forceinline__ void bind(void *base, unsigned sz, void *vals_base) {
+        size = sz;
+        keys = reinterpret_cast<int *>(base);
+        ent = reinterpret_cast<unsigned long long *>(base);
+        vals = reinterpret_cast<T *>(vals_base);
+    }
+    static __host__ __device__ constexpr size_t entry_bytes() { return NUMERIC ? (kPacked ? 8 : 4 + sizeof(T)) : 4; }
+    __device__ __forceinline__ void init(const SR &sr, int tid, int nthreads) {
+        for (unsigned t = tid; t < size; t += nthreads) {
+            if (kPacked) ent[t] = HASH_EMPTY64;
+            else {
+                keys[t] = HASH_EMPTY;
+                if (NUMERIC) vals[t] = sr.identity();
+            }
+        }
+    }
+    // returns 1 when the key was new
+    __device__ __forceinline__ int insert(const SR &sr, int j, T p) {
+        unsigned h = hash_slot(j, size);
+        if (kPacked) {
+            const unsigned long long mine = pack_entry<T>(j, p);
+            while (true) {
+                unsigned long long cur = ent[h];
+                if (cur == HASH_EMPTY64) {
+                    cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
+                    if (cur == HASH_EMPTY64) return 1;
+                }
+                if ((int)(cur >> 32) == j) {
+                    atomic_combine(sr, reinterpret_cast<T *>(&ent[h]), p);   // value half (little endian: low word)
+                    return 0;
+                }
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        } else {
+            while (true) {
+                int cur = keys[h];
+                int fresh = 0;
+                if (cur == HASH_EMPTY) {
+                    cur = atomicCAS(&keys[h], HASH_EMPTY, j);
+                    if (cur == HASH_EMPTY) { fresh = 1; cur = j; }
+                }
+                if (cur == j) {
+                    if (NUMERIC) atomic_combine(sr, &vals[h], p);
+                    return fresh;
+                }
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        }
+    }
+    // copy every occupied slot to out[*count ...] (count is a shared-memory counter)
+    __device__ __forceinline__ void drain(int tid, int nthreads, int *count, int32_t *__restrict__ oj, T *__restrict__ ox) {
+        for (unsigned t = tid; t < size; t += nthreads) {
+            if (kPacked) {
+                const unsigned long long e = ent[t];
+                if (e != HASH_EMPTY64) {
+                    const int pos = atomicAdd(count, 1);
+                    oj[pos] = (int)(e >> 32);
+                    ox[pos] = unpack_value<T>(e);
+                }
+            } else {
+                const int key = keys[t];
+                if (key != HASH_EMPTY) {
+                    const int pos = atomicAdd(count, 1);
+                    oj[pos] = key;
+                    ox[pos] = vals[t];
+                }
+            }
+        }
+    }
+};
 
 // ------------------------------------------------------------------ flops per row
 __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj,
@@ -48,99 +152,95 @@ __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, 
 }
 
 // ------------------------------------------------------------------ binning
-constexpr int NBINS = 10;
-// bin b holds rows with count in (kBinMax[b-1], kBinMax[b]]; bin 0 = empty rows; bin 9 = global-table rows
-__constant__ int64_t c_bin_max[NBINS] = {0, 32, 128, 256, 512, 1024, 2048, 4096, 8192, INT64_MAX};
-static const int h_bin_table[NBINS] = {0, 64, 256, 512, 1024, 2048, 4096, 8192, 16384, 0};
-static const int h_bin_threads[NBINS] = {0, 256, 256, 64, 128, 128, 256, 256, 512, 512};
+constexpr int NBINS = 11;   // 0: empty rows, 1-2: warp per row, 3-9: CTA per row (shared table), 10: global table
+struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int tf8; };
 
-__device__ __forceinline__ int bin_of(int64_t c) {
+static BinSpec make_bin_spec(size_t entry_bytes) {
+    BinSpec s;
+    const int caps[NBINS] = {0, 64, 256, 512, 1024, 2048, 4096, 8192, 16384, 0, 0};
+    const int thr[NBINS] = {0, 256, 256, 128, 128, 256, 256, 256, 512, 512, 512};
+    int maxcap = (int)((212 * 1024) / entry_bytes);   // 227 KB minus the kernel's static arrays
+    maxcap -= maxcap % 256;
+    for (int b = 0; b < NBINS; b++) { s.cap[b] = caps[b]; s.threads[b] = thr[b]; }
+    s.cap[9] = maxcap > 16384 + 2048 ? maxcap : 16384;
+    s.cap[10] = 0;
+    s.maxcount[0] = 0;
+    s.tf8 = (int)opt_get_int("spgemm_table_factor8", 20);   // table = tf8/8 x count
+    if (s.tf8 < 10) s.tf8 = 10;
+    for (int b = 1; b <= 9; b++) s.maxcount[b] = (((int64_t)s.cap[b] - 8) * 8) / s.tf8 - 1;   // tf8/8*count + 8 <= cap
+    if (s.cap[9] == 16384) s.maxcount[9] = s.maxcount[8];                            // bin 9 unused
+    s.maxcount[10] = INT64_MAX;
+    return s;
+}
+__device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
     int b = 0;
 #pragma unroll
-    for (int q = 0; q < NBINS - 1; q++) b += (c > c_bin_max[q]);
+    for (int q = 0; q < NBINS - 1; q++) b += (c > s.maxcount[q]);
     return b;
 }
-__global__ void bin_count_kernel(int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ bin_counts) {
+__global__ void bin_count_kernel(BinSpec spec, int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ bin_counts) {
     __shared__ unsigned int s[NBINS];
     if (threadIdx.x < NBINS) s[threadIdx.x] = 0;
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nrows; i += stride) atomicAdd(&s[bin_of(cnt[i])], 1u);
+    for (; i < nrows; i += stride) atomicAdd(&s[bin_of(spec, cnt[i])], 1u);
     __syncthreads();
     if (threadIdx.x < NBINS && s[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], (unsigned long long)s[threadIdx.x]);
 }
-__global__ void bin_fill_kernel(int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ cursors,
+// two-level: CTA-local histogram + one global atomic per (CTA, bin) reserves a contiguous range
+__global__ void bin_fill_kernel(BinSpec spec, int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ cursors,
                                 int32_t *__restrict__ bin_rows) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nrows; i += stride) {
-        int b = bin_of(cnt[i]);
-        if (b == 0) continue;
-        unsigned long long pos = atomicAdd(&cursors[b], 1ull);
-        bin_rows[pos] = (int32_t)i;
+    __shared__ unsigned int s_cnt[NBINS];
+    __shared__ unsigned long long s_base[NBINS];
+    const int64_t per_block = ((nrows + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per_block;
+    const int64_t hi = lo + per_block < nrows ? lo + per_block : nrows;
+    if (threadIdx.x < NBINS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int b = bin_of(spec, cnt[i]);
+        if (b) atomicAdd(&s_cnt[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NBINS) {
+        s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int b = bin_of(spec, cnt[i]);
+        if (b) bin_rows[s_base[b] + atomicAdd(&s_cnt[b], 1u)] = (int32_t)i;
     }
 }
 
-// ------------------------------------------------------------------ the hash kernels
-// One "group" (a warp when WARP_ROWS, else the whole CTA) owns one row and one hash table.
-template <typename SR, typename T, bool NUMERIC, bool WARP_ROWS>
-__global__ void spgemm_hash_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int table_size, int shift,
-                                   const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
-                                   const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
-                                   int64_t *__restrict__ row_nnz,       // symbolic output
-                                   const int64_t *__restrict__ Cp, int32_t *__restrict__ Cj, T *__restrict__ Cx,  // numeric output
-                                   int *g_keys, T *g_vals, const int64_t *__restrict__ g_offsets) {
+// ------------------------------------------------------------------ warp-per-row kernel (tiny rows)
+template <typename SR, typename T, bool NUMERIC, bool PACK>
+__global__ void __launch_bounds__(256)
+spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+                   const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                   const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                   int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox) {
+    typedef HashTable<SR, T, NUMERIC, PACK> Table;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int group_threads = WARP_ROWS ? 32 : blockDim.x;
-    const int gtid = WARP_ROWS ? (threadIdx.x & 31) : threadIdx.x;
-    const int groups_per_block = WARP_ROWS ? (blockDim.x >> 5) : 1;
-    const int group_in_block = WARP_ROWS ? (threadIdx.x >> 5) : 0;
-    const int64_t g = (int64_t)blockIdx.x * groups_per_block + group_in_block;
-    const bool active = g < n_rows;   // whole group shares this predicate
-    __shared__ int s_count_blk;
-
-    int *keys;
-    T *vals = nullptr;
-    int *count;
-    int tsize = table_size, tshift = shift;
-    if (g_keys) {   // global-memory table for this row
-        int64_t off = active ? g_offsets[g] : 0;
-        int64_t sz = active ? g_offsets[g + 1] - off : 2;
-        keys = g_keys + off;
-        if (NUMERIC) vals = g_vals + off;
-        tsize = (int)sz;
-        tshift = 32 - (31 - __clz((unsigned)tsize));
-        count = &s_count_blk;
-    } else if (WARP_ROWS) {
-        const size_t per = (size_t)table_size * (NUMERIC ? (4 + sizeof(T)) : 4) + 8;
-        unsigned char *base = s_raw + ((per + 7) & ~(size_t)7) * group_in_block;
-        count = reinterpret_cast<int *>(base);
-        keys = reinterpret_cast<int *>(base + 8);
-        if (NUMERIC) vals = reinterpret_cast<T *>(base + 8 + (size_t)table_size * 4);
-    } else {
-        count = &s_count_blk;
-        keys = reinterpret_cast<int *>(s_raw);
-        if (NUMERIC) vals = reinterpret_cast<T *>(s_raw + (size_t)table_size * 4);
-    }
-    const int mask = tsize - 1;
-
-    // init
-    if (active) {
-        for (int t = gtid; t < tsize; t += group_threads) {
-            keys[t] = HASH_EMPTY;
-            if (NUMERIC) vals[t] = sr.identity();
-        }
-    }
-    if (gtid == 0) *count = 0;
-    if (WARP_ROWS) __syncwarp(); else __syncthreads();
-
+    const int lane32 = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const bool active = g < n_rows;
+    const size_t per = (((size_t)cap * Table::entry_bytes() + 8) + 15) & ~(size_t)15;
+    unsigned char *base = s_raw + per * wib;
+    int *count = reinterpret_cast<int *>(base);
+    Table tab;
+    const int64_t row = active ? rows[g] : 0;
+    const unsigned tsize = active ? (unsigned)table_size_for(cnt[row], cap, tf8) : 32u;
+    tab.bind(base + 8, tsize, base + 8 + (size_t)cap * 4);
+    if (active) tab.init(sr, lane32, 32);
+    if (lane32 == 0) *count = 0;
+    __syncwarp();
     int local_new = 0;
     if (active) {
-        const int64_t row = rows[g];
-        const int sub = gtid / LPE, lane = gtid % LPE, nsub = group_threads / LPE;
+        const int sub = lane32 / LPE, lane = lane32 % LPE;
         const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
-        for (int64_t k = a_beg + sub; k < a_end; k += nsub) {
+        for (int64_t k = a_beg + sub; k < a_end; k += 32 / LPE) {
             const int32_t br = Aj[k];
             T a = one_of<T>();
             if (NUMERIC && sr.reads_a()) a = Ax[k];
@@ -148,53 +248,133 @@ __global__ void spgemm_hash_kernel(SR sr, const int32_t *__restrict__ rows, int6
             for (int64_t q = b_beg + lane; q < b_end; q += LPE) {
                 const int j = Bj[q];
                 T p = T();
-                if (NUMERIC) {
-                    T b = sr.reads_b() ? Bx[q] : one_of<T>();
-                    p = sr.mul(a, b);
-                }
-                unsigned h = hash_slot(j, tshift) & (unsigned)mask;
-                while (true) {
-                    int cur = keys[h];
-                    if (cur == HASH_EMPTY) {
-                        cur = atomicCAS(&keys[h], HASH_EMPTY, j);
-                        if (cur == HASH_EMPTY) { local_new++; cur = j; }
-                    }
-                    if (cur == j) {
-                        if (NUMERIC) atomic_combine(sr, &vals[h], p);
-                        break;
-                    }
-                    h = (h + 1) & (unsigned)mask;
-                }
+                if (NUMERIC) p = sr.mul(a, sr.reads_b() ? Bx[q] : one_of<T>());
+                local_new += tab.insert(sr, j, p);
             }
         }
     }
-
-    if (!NUMERIC) {
-        // row_nnz = number of successful first inserts
+    __syncwarp();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) local_new += __shfl_down_sync(0xffffffffu, local_new, o);
-        if (WARP_ROWS) {
-            if (gtid == 0 && active) row_nnz[rows[g]] = local_new;
-        } else {
-            if ((threadIdx.x & 31) == 0 && local_new) atomicAdd(count, local_new);
-            __syncthreads();
-            if (threadIdx.x == 0 && active) row_nnz[rows[g]] = *count;
+    for (int o = 16; o > 0; o >>= 1) local_new += __shfl_down_sync(0xffffffffu, local_new, o);
+    if (active) {
+        if (lane32 == 0 && row_nnz) row_nnz[row] = local_new;
+        if (NUMERIC) {
+            const int64_t ob = Op[row];
+            tab.drain(lane32, 32, count, Oj + ob, Ox + ob);
         }
-        return;
+    }
+}
+
+// ------------------------------------------------------------------ CTA-per-row kernel, products flattened per thread
+// The A row is staged in shared memory a chunk (blockDim entries) at a time: B-row start, A value and the exclusive
+// prefix of the B-row lengths.  The chunk's products form one index space [0, P); thread t takes products
+// t, t+blockDim, ... (consecutive lanes -> consecutive entries of the same B row -> coalesced loads), finds the
+// owning A entry with a binary search on the prefix (lanes of a warp follow almost the same search path, so the
+// shared-memory reads broadcast), issues UNROLL independent loads, then inserts.  Every lane has work regardless of
+// how short the B rows are.  GLOBAL selects a global-memory table (rows too big for shared memory); it is a
+// template parameter so that the shared-memory instantiation compiles to ATOMS/LDS/STS rather than generic atomics.
+constexpr int UNROLL = 4;
+template <typename SR, typename T, bool NUMERIC, bool PACK, bool GLOBAL>
+__global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+                                    const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                                    const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                                    int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
+                                    T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets) {
+    typedef HashTable<SR, T, NUMERIC, PACK> Table;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int64_t s_bs[MAX_THREADS];
+    __shared__ int s_off[MAX_THREADS + 1];
+    __shared__ T s_av[MAX_THREADS];
+    __shared__ int s_wsum[MAX_THREADS / 32];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int64_t row = rows[blockIdx.x];
+
+    Table tab;
+    if (GLOBAL) {   // global-memory table: [offset, offset + size) entries of this row
+        const int64_t off = g_offsets[blockIdx.x];
+        const unsigned sz = (unsigned)(g_offsets[blockIdx.x + 1] - off);
+        const int64_t total = g_offsets[gridDim.x];
+        unsigned char *kbase = g_table + (size_t)off * (Table::kPacked ? 8 : 4);
+        unsigned char *vbase = g_table + (size_t)total * 4 + (size_t)off * sizeof(T);
+        tab.bind(kbase, sz, vbase);
     } else {
-        if (WARP_ROWS) __syncwarp(); else __syncthreads();
-        if (active) {
-            const int64_t row = rows[g];
-            const int64_t base = Cp[row];
-            for (int t = gtid; t < tsize; t += group_threads) {
-                int key = keys[t];
-                if (key != HASH_EMPTY) {
-                    int pos = atomicAdd(count, 1);
-                    Cj[base + pos] = key;
-                    Cx[base + pos] = vals[t];
+        tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4);
+    }
+    tab.init(sr, tid, nthreads);
+    if (tid == 0) s_count = 0;
+
+    const int wlane = tid & 31, warp = tid >> 5;
+    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
+    int local_new = 0;
+    for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
+        const int chunk_n = (int)((a_end - c0 < nthreads) ? (a_end - c0) : nthreads);
+        int len = 0;
+        if (tid < chunk_n) {
+            const int64_t k = c0 + tid;
+            const int32_t br = Aj[k];
+            const int64_t bs = Bp[br];
+            len = (int)(Bp[br + 1] - bs);
+            s_bs[tid] = bs;
+            if (NUMERIC && sr.reads_a()) s_av[tid] = Ax[k];
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (wlane >= o) incl += up;
+        }
+        if (wlane == 31) s_wsum[warp] = incl;
+        __syncthreads();   // also orders the table init / the previous chunk's inserts before this chunk's
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_wsum[w];
+        s_off[tid] = base + incl - len;
+        if (tid == nthreads - 1) s_off[nthreads] = base + incl;
+        __syncthreads();
+        const int P = s_off[nthreads];
+        for (int p0 = tid; p0 < P; p0 += nthreads * UNROLL) {
+            int jj[UNROLL];
+            T bb[UNROLL], aa[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const int p = p0 + u * nthreads;
+                jj[u] = HASH_EMPTY;
+                if (p < P) {
+                    int lo = 0, hi = chunk_n - 1;   // last entry e with s_off[e] <= p (zero-length rows are skipped)
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_off[mid] <= p) lo = mid;
+                        else hi = mid - 1;
+                    }
+                    const int64_t q = s_bs[lo] + (p - s_off[lo]);
+                    jj[u] = Bj[q];
+                    if (NUMERIC && sr.reads_b()) bb[u] = Bx[q];
+                    if (NUMERIC && sr.reads_a()) aa[u] = s_av[lo];
                 }
             }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (jj[u] == HASH_EMPTY) continue;
+                T pr = T();
+                if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                local_new += tab.insert(sr, jj[u], pr);
+            }
         }
+        __syncthreads();   // s_* arrays are rewritten by the next chunk
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_new += __shfl_down_sync(0xffffffffu, local_new, o);
+    if (NUMERIC) {
+        const int64_t ob = Op[row];
+        tab.drain(tid, nthreads, &s_count, Oj + ob, Ox + ob);
+        if (row_nnz) {
+            __syncthreads();
+            if (tid == 0) row_nnz[row] = s_count;
+        }
+    } else {
+        if (wlane == 0 && local_new) atomicAdd(&s_count, local_new);
+        __syncthreads();
+        if (tid == 0) row_nnz[row] = s_count;
     }
 }
 
@@ -202,10 +382,8 @@ __global__ void gtable_sizes_kernel(const int32_t *__restrict__ rows, int64_t n,
                                     int64_t *__restrict__ sizes) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t c = cnt[rows[i]] * 2;
-    int64_t s = 1024;
-    while (s < c) s <<= 1;
-    sizes[i] = s;
+    int64_t c = cnt[rows[i]];
+    sizes[i] = (2 * c + 1024) & ~(int64_t)3;   // multiple of 4 keeps the value array 16-byte aligned
 }
 __global__ void i64_copy_kernel(int64_t *dst, const int64_t *src, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,15 +402,40 @@ __global__ void reduce_sum_max_kernel(const int64_t *__restrict__ v, int64_t n, 
     }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); }
 }
+// staging (addressed by the flops prefix) -> final CSR: one warp per row, coalesced both ways, 4 loads in flight
+template <typename T>
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(int64_t nrows, const int64_t *__restrict__ Sp, const int64_t *__restrict__ Cp,
+                    const int32_t *__restrict__ Sj, const T *__restrict__ Sx, int32_t *__restrict__ Cj, T *__restrict__ Cx) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w; i < nrows; i += nw) {
+        const int64_t src = Sp[i], dst = Cp[i], n = Cp[i + 1] - dst;
+        int64_t k = lane;
+        for (; k + 96 < n; k += 128) {
+            int32_t j0 = __ldcs(Sj + src + k), j1 = __ldcs(Sj + src + k + 32), j2 = __ldcs(Sj + src + k + 64), j3 = __ldcs(Sj + src + k + 96);
+            T x0 = __ldcs(Sx + src + k), x1 = __ldcs(Sx + src + k + 32), x2 = __ldcs(Sx + src + k + 64), x3 = __ldcs(Sx + src + k + 96);
+            Cj[dst + k] = j0; Cj[dst + k + 32] = j1; Cj[dst + k + 64] = j2; Cj[dst + k + 96] = j3;
+            Cx[dst + k] = x0; Cx[dst + k + 32] = x1; Cx[dst + k + 64] = x2; Cx[dst + k + 96] = x3;
+        }
+        for (; k < n; k += 32) {
+            Cj[dst + k] = __ldcs(Sj + src + k);
+            Cx[dst + k] = __ldcs(Sx + src + k);
+        }
+    }
+}
 
 // ------------------------------------------------------------------ host orchestration
 struct Bins {
     int32_t *rows = nullptr;           // row ids grouped by bin
     unsigned long long count[NBINS];   // rows per bin
     unsigned long long start[NBINS];   // offset of each bin inside rows[]
+    BinSpec spec;
 };
 
-static GrB_Info make_bins(Bins *bins, int64_t nrows, const int64_t *cnt, std::string *err) {
+static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const int64_t *cnt, std::string *err) {
+    bins->spec = make_bin_spec(entry_bytes);
     unsigned long long *d = dev_alloc_t<unsigned long long>(2 * NBINS);
     bins->rows = dev_alloc_t<int32_t>((size_t)(nrows > 0 ? nrows : 1));
     if (!d || !bins->rows) { dev_free(d); dev_free(bins->rows); bins->rows = nullptr; return set_error(err, GrB_OUT_OF_MEMORY, "spgemm bins"); }
@@ -240,7 +443,7 @@ static GrB_Info make_bins(Bins *bins, int64_t nrows, const int64_t *cnt, std::st
     int blocks = (int)std::min<int64_t>((nrows + 255) / 256 + 1, (int64_t)g_num_sms * 8);
     {
         LAUNCH_NOTE("spgemm_bin_count");
-        bin_count_kernel<<<blocks, 256, 0, g_stream>>>(nrows, cnt, d);
+        bin_count_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d);
     }
     cudaMemcpyAsync(bins->count, d, sizeof(unsigned long long) * NBINS, cudaMemcpyDeviceToHost, g_stream);
     cudaStreamSynchronize(g_stream);
@@ -253,7 +456,7 @@ static GrB_Info make_bins(Bins *bins, int64_t nrows, const int64_t *cnt, std::st
     cudaMemcpyAsync(d + NBINS, cursors, sizeof(cursors), cudaMemcpyHostToDevice, g_stream);
     {
         LAUNCH_NOTE("spgemm_bin_fill");
-        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(nrows, cnt, d + NBINS, bins->rows);
+        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d + NBINS, bins->rows);
     }
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(g_stream);   // `cursors` is a host stack array read by the async copy
@@ -265,43 +468,35 @@ static GrB_Info make_bins(Bins *bins, int64_t nrows, const int64_t *cnt, std::st
 struct HashArgs {
     const int64_t *Ap; const int32_t *Aj; const void *Ax;
     const int64_t *Bp; const int32_t *Bj; const void *Bx;
-    int64_t *row_nnz; const int64_t *Cp; int32_t *Cj; void *Cx;
-    const int64_t *cnt;   // per-row bound (flops or nnz) used for global table sizing
+    int64_t *row_nnz;                  // written when non-null (symbolic count, or exact count of a one-pass row)
+    const int64_t *Op; int32_t *Oj; void *Ox;   // numeric output: row i's entries go to O*[Op[i] ...]
+    const int64_t *cnt;                // per-row bound the bins / table sizes were derived from
 };
 
-template <typename SR, typename T, bool NUMERIC>
+template <typename SR, typename T, bool NUMERIC, bool PACK>
 static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std::string *err) {
-    const size_t entry = NUMERIC ? 4 + sizeof(T) : 4;
+    typedef HashTable<SR, T, NUMERIC, PACK> Table;
+    const size_t entry = Table::entry_bytes();
+    const char *phase = NUMERIC ? "numeric" : "symbolic";
     for (int b = 1; b < NBINS; b++) {
         const int64_t n = (int64_t)bins.count[b];
         if (n == 0) continue;
         const int32_t *rows = bins.rows + bins.start[b];
-        if (b < NBINS - 1) {
-            const int table = h_bin_table[b], threads = h_bin_threads[b];
-            int shift = 32;
-            for (int s = table; s > 1; s >>= 1) shift--;
-            const bool warp_rows = (b <= 2);
-            if (warp_rows) {
-                const int rpb = threads / 32;
-                size_t per = (((size_t)table * entry + 8) + 7) & ~(size_t)7;
-                size_t smem = per * rpb;
-                auto kern = spgemm_hash_kernel<SR, T, NUMERIC, true>;
-                if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
-                kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, table, shift, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Cp, a.Cj, (T *)a.Cx, nullptr, nullptr, nullptr);
-            } else {
-                size_t smem = (size_t)table * entry;
-                auto kern = spgemm_hash_kernel<SR, T, NUMERIC, false>;
-                if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
-                kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, n, table, shift, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Cp, a.Cj, (T *)a.Cx, nullptr, nullptr, nullptr);
-            }
-            {
-                cudaError_t le = cudaGetLastError();
-                if (le != cudaSuccess)
-                    return set_error(err, GrB_PANIC, "spgemm %s kernel launch failed in bin %d (table %d, %d threads, %lld rows, entry %zu B): %s",
-                                     NUMERIC ? "numeric" : "symbolic", b, table, threads, (long long)n, entry, cudaGetErrorString(le));
-            }
+        const int cap = bins.spec.cap[b], threads = bins.spec.threads[b];
+        if (b <= 2) {
+            const int rpb = threads / 32;
+            const size_t per = (((size_t)cap * entry + 8) + 15) & ~(size_t)15;
+            const size_t smem = per * rpb;
+            auto kern = spgemm_warp_kernel<SR, T, NUMERIC, PACK>;
+            if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
+            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+        } else if (b < NBINS - 1) {
+            const size_t smem = (size_t)cap * entry;
+            auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
+            if (smem > 32 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
+            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr);
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
@@ -312,6 +507,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             std::vector<int64_t> hs((size_t)n + 1);
             cudaMemcpyAsync(hs.data(), sizes, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, g_stream);
             cudaStreamSynchronize(g_stream);
+            dev_free(sizes);
             int64_t i0 = 0;
             GrB_Info info = GrB_SUCCESS;
             while (i0 < n && !info) {
@@ -321,23 +517,25 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 offs[0] = 0;
                 for (int64_t q = i0; q < i1; q++) offs[(size_t)(q - i0) + 1] = offs[(size_t)(q - i0)] + hs[(size_t)q];
                 int64_t *doffs = dev_alloc_t<int64_t>(offs.size());
-                int *gk = dev_alloc_t<int>((size_t)tot);
-                T *gv = NUMERIC ? dev_alloc_t<T>((size_t)tot) : nullptr;
-                if (!doffs || !gk || (NUMERIC && !gv)) info = set_error(err, GrB_OUT_OF_MEMORY, "global hash tables (%lld entries)", (long long)tot);
+                // packed / symbolic: one array of `tot` entries; split numeric: tot keys (4 B) then tot values
+                const size_t bytes = Table::kPacked ? (size_t)tot * 8 : (size_t)tot * 4 + (NUMERIC ? (size_t)tot * sizeof(T) + 16 : 0);
+                unsigned char *gt = (unsigned char *)dev_alloc(bytes);
+                if (!doffs || !gt) info = set_error(err, GrB_OUT_OF_MEMORY, "global hash tables (%lld entries)", (long long)tot);
                 if (!info) {
                     cudaMemcpyAsync(doffs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, g_stream);
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_hash_kernel<SR, T, NUMERIC, false><<<(unsigned)(i1 - i0), 512, 0, g_stream>>>(sr, rows + i0, i1 - i0, 2, 31, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Cp, a.Cj, (T *)a.Cx, gk, gv, doffs);
-                    cudaError_t e = cudaGetLastError();
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 512, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs);
                     cudaStreamSynchronize(g_stream);   // offs is host memory
-                    if (e != cudaSuccess) info = cuda_fail(err, e, "spgemm global-table kernel");
                 }
-                dev_free(doffs); dev_free(gk); dev_free(gv);
+                dev_free(doffs); dev_free(gt);
                 i0 = i1;
             }
-            dev_free(sizes);
             GRB_TRY(info);
         }
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess)
+            return set_error(err, GrB_PANIC, "spgemm %s kernel launch failed in bin %d (cap %d, %d threads, %lld rows, entry %zu B): %s",
+                             phase, b, cap, threads, (long long)n, entry, cudaGetErrorString(le));
     }
     return GrB_SUCCESS;
 }
@@ -348,9 +546,13 @@ struct SpgemmPlan {
     int a_type, b_type;
 };
 
+static bool use_packed() { return opt_get_int("spgemm_pack", 1) != 0; }
+template <typename T> static size_t numeric_entry_bytes() { return (Packed<T>::value && use_packed()) ? 8 : 4 + sizeof(T); }
+
+// numeric pass writing row i at O*[Op[i]...]; row_nnz (optional) receives exact counts
 template <typename T>
-static GrB_Info spgemm_numeric_typed(GrB_Matrix Tm, const GrB_Semiring op, const SpgemmPlan &p, const Bins &bins,
-                                     const int64_t *row_nnz, std::string *err) {
+static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p, const Bins &bins, const int64_t *cnt,
+                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, std::string *err) {
     GrB_Info info = GrB_SUCCESS;
     const int T_code = type_code_of<T>();
     GRB_DISPATCH_SEMIRING(op->add, op->mul, T, SRT, sr, {
@@ -359,13 +561,21 @@ static GrB_Info spgemm_numeric_typed(GrB_Matrix Tm, const GrB_Semiring op, const
         if (sr.reads_a()) info = cast_view(&ax, &atmp, p.A->val, p.a_type, T_code, p.annz, err);
         if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
         if (!info) {
-            HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, nullptr, Tm->csr.ptr, Tm->csr.idx, Tm->csr.val, row_nnz};
-            info = run_bins<SRT, T, true>(sr, bins, a, err);
+            HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt};
+            if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
+            else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
         }
         dev_free(atmp);
         dev_free(btmp);
     });
     return info;
+}
+
+template <typename T>
+static void launch_compact(int64_t m, const int64_t *Sp, const int64_t *Cp, const int32_t *Sj, const void *Sx, int32_t *Cj, void *Cx) {
+    int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)g_num_sms * 32);
+    LAUNCH_NOTE("spgemm_compact");
+    compact_rows_kernel<T><<<blocks, 256, 0, g_stream>>>(m, Sp, Cp, Sj, (const T *)Sx, Cj, (T *)Cx);
 }
 
 GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, GrB_Matrix B, bool bt, const GrB_Matrix M,
@@ -388,17 +598,24 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     if (p.k != bk)
         return set_error(err, GrB_DIMENSION_MISMATCH, "mxm: inner dimensions differ (%lld vs %lld)", (long long)p.k, (long long)bk);
     const int D = op ? op->type : TC_INT64;
+    const size_t es = type_size(D);
 
     int64_t *flops = dev_alloc_t<int64_t>((size_t)p.m + 1), *row_nnz = dev_alloc_t<int64_t>((size_t)p.m + 1);
+    int64_t *Sp = nullptr;
+    int32_t *Sj = nullptr;
+    void *Sx = nullptr;
     unsigned long long *red = dev_alloc_t<unsigned long long>(2);
-    Bins sbins, nbins;
+    Bins fbins, nbins;
     GrB_Matrix Tm = nullptr;
     GrB_Info info = GrB_SUCCESS;
     if (!flops || !row_nnz || !red) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm row arrays");
     unsigned long long hred[2] = {0, 0};
-    if (!info && p.m > 0) {
+    if (!info) {
         cudaMemsetAsync(red, 0, 16, g_stream);
         cudaMemsetAsync(row_nnz, 0, sizeof(int64_t) * ((size_t)p.m + 1), g_stream);
+        cudaMemsetAsync(flops, 0, sizeof(int64_t) * ((size_t)p.m + 1), g_stream);
+    }
+    if (!info && p.m > 0) {
         int blocks = (int)std::min<int64_t>((p.m + 31) / 32, (int64_t)g_num_sms * 32);
         {
             LAUNCH_NOTE("spgemm_row_flops");
@@ -409,17 +626,23 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             reduce_sum_max_kernel<<<std::min(blocks, g_num_sms * 4), 256, 0, g_stream>>>(flops, p.m, red);
         }
         cudaMemcpyAsync(hred, red, 16, cudaMemcpyDeviceToHost, g_stream);
-        info = make_bins(&sbins, p.m, flops, err);
+        cudaStreamSynchronize(g_stream);
     }
-    if (flops_out) *flops_out = hred[0];
-    // ---- symbolic
-    if (!info && p.m > 0) {
-        HashArgs a{p.A->ptr, p.A->idx, nullptr, p.B->ptr, p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops};
-        SRDyn<int32_t> dummy;
-        dummy.a_op = OP_ANY; dummy.m_op = OP_PAIR;
-        info = run_bins<SRDyn<int32_t>, int32_t, false>(dummy, sbins, a, err);
+    const uint64_t total_flops = hred[0];
+    if (flops_out) *flops_out = total_flops;
+
+    // one pass (no symbolic phase) when the flops-sized staging copy plus the result fit comfortably
+    bool onepass = false;
+    if (!info && !symbolic_only && total_flops > 0) {
+        const char *mode = opt_get("spgemm_mode", "auto");
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double need = 2.0 * (double)total_flops * (double)(4 + es);
+        const double avail = (double)total_b * 0.9 - (double)GrB_cuda_memory_in_use();
+        onepass = !strcmp(mode, "onepass") || (!strcmp(mode, "auto") && need < 0.8 * avail);
+        if (!strcmp(mode, "twopass")) onepass = false;
     }
-    int64_t total = 0;
+
     if (!info) {
         GrB_Info i2 = matrix_new_shell(&Tm, D, p.m, p.n);
         if (i2) info = i2;
@@ -428,28 +651,91 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         Tm->csr.ptr = dev_alloc_t<int64_t>((size_t)p.m + 1);
         if (!Tm->csr.ptr) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm row pointers");
     }
-    if (!info) {
-        note_launch("i64_copy");
-        i64_copy_kernel<<<(unsigned)std::min<int64_t>((p.m + 256) / 256, (int64_t)g_num_sms * 8), 256, 0, g_stream>>>(Tm->csr.ptr, row_nnz, p.m + 1);
-        info = exclusive_scan_i64(Tm->csr.ptr, p.m + 1, err);
-        if (!info) total = read_i64(Tm->csr.ptr + p.m);
-    }
-    if (nvals_out) *nvals_out = (uint64_t)total;
-    if (!info && !symbolic_only) {
-        size_t nv = (size_t)(total > 0 ? total : 1);
-        Tm->csr.idx = dev_alloc_t<int32_t>(nv);
-        Tm->csr.val = dev_alloc(nv * type_size(D));
-        Tm->nvals = total;
-        Tm->jumbled = true;
-        if (!Tm->csr.idx || !Tm->csr.val) info = set_error(err, GrB_OUT_OF_MEMORY, "mxm result needs %lld entries (%.1f GB)", (long long)total, (double)total * (4 + type_size(D)) / 1e9);
-        if (!info && total > 0) info = make_bins(&nbins, p.m, row_nnz, err);
-        if (!info && total > 0) {
+    int64_t total = 0;
+    const unsigned copy_blocks = (unsigned)std::min<int64_t>((p.m + 256) / 256, (int64_t)g_num_sms * 8);
+
+    if (!info && onepass) {
+        // ---- bins and tables from the flops bound; staging addressed by the flops prefix
+        size_t entry = 12;
+        GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
+        info = make_bins(&fbins, entry, p.m, flops, err);
+        if (!info) {
+            Sp = dev_alloc_t<int64_t>((size_t)p.m + 1);
+            Sj = dev_alloc_t<int32_t>((size_t)total_flops);
+            Sx = dev_alloc((size_t)total_flops * es);
+            if (!Sp || !Sj || !Sx) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm staging (%llu products)", (unsigned long long)total_flops);
+        }
+        if (!info) {
+            note_launch("i64_copy");
+            i64_copy_kernel<<<copy_blocks, 256, 0, g_stream>>>(Sp, flops, p.m + 1);
+            info = exclusive_scan_i64(Sp, p.m + 1, err);
+        }
+        if (!info) {
             GrB_Info i3 = GrB_NOT_IMPLEMENTED;
-            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(Tm, op, p, nbins, row_nnz, err));
+            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, flops, row_nnz, Sp, Sj, Sx, err));
             info = i3;
         }
+        if (!info) {
+            note_launch("i64_copy");
+            i64_copy_kernel<<<copy_blocks, 256, 0, g_stream>>>(Tm->csr.ptr, row_nnz, p.m + 1);
+            info = exclusive_scan_i64(Tm->csr.ptr, p.m + 1, err);
+            if (!info) total = read_i64(Tm->csr.ptr + p.m);
+        }
+        if (!info) {
+            size_t nv = (size_t)(total > 0 ? total : 1);
+            Tm->csr.idx = dev_alloc_t<int32_t>(nv);
+            Tm->csr.val = dev_alloc(nv * es);
+            Tm->nvals = total;
+            Tm->jumbled = true;
+            if (!Tm->csr.idx || !Tm->csr.val) info = set_error(err, GrB_OUT_OF_MEMORY, "mxm result needs %lld entries (%.1f GB)", (long long)total, (double)total * (4 + es) / 1e9);
+        }
+        if (!info && total > 0) {
+            switch (es) {
+                case 1: launch_compact<uint8_t>(p.m, Sp, Tm->csr.ptr, Sj, Sx, Tm->csr.idx, Tm->csr.val); break;
+                case 2: launch_compact<uint16_t>(p.m, Sp, Tm->csr.ptr, Sj, Sx, Tm->csr.idx, Tm->csr.val); break;
+                case 4: launch_compact<uint32_t>(p.m, Sp, Tm->csr.ptr, Sj, Sx, Tm->csr.idx, Tm->csr.val); break;
+                default: launch_compact<uint64_t>(p.m, Sp, Tm->csr.ptr, Sj, Sx, Tm->csr.idx, Tm->csr.val); break;
+            }
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) info = cuda_fail(err, e, "spgemm compaction");
+        }
+    } else if (!info) {
+        // ---- two-pass: symbolic count, exact allocation, numeric
+        if (p.m > 0 && total_flops > 0) {
+            info = make_bins(&fbins, 4, p.m, flops, err);
+            if (!info) {
+                HashArgs a{p.A->ptr, p.A->idx, nullptr, p.B->ptr, p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops};
+                SRDyn<int32_t> dummy;
+                dummy.a_op = OP_ANY; dummy.m_op = OP_PAIR;
+                info = run_bins<SRDyn<int32_t>, int32_t, false, false>(dummy, fbins, a, err);
+            }
+        }
+        if (!info) {
+            note_launch("i64_copy");
+            i64_copy_kernel<<<copy_blocks, 256, 0, g_stream>>>(Tm->csr.ptr, row_nnz, p.m + 1);
+            info = exclusive_scan_i64(Tm->csr.ptr, p.m + 1, err);
+            if (!info) total = read_i64(Tm->csr.ptr + p.m);
+        }
+        if (!info && !symbolic_only) {
+            size_t nv = (size_t)(total > 0 ? total : 1);
+            Tm->csr.idx = dev_alloc_t<int32_t>(nv);
+            Tm->csr.val = dev_alloc(nv * es);
+            Tm->nvals = total;
+            Tm->jumbled = true;
+            if (!Tm->csr.idx || !Tm->csr.val) info = set_error(err, GrB_OUT_OF_MEMORY, "mxm result needs %lld entries (%.1f GB)", (long long)total, (double)total * (4 + es) / 1e9);
+            size_t entry = 12;
+            GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
+            if (!info && total > 0) info = make_bins(&nbins, entry, p.m, row_nnz, err);
+            if (!info && total > 0) {
+                GrB_Info i3 = GrB_NOT_IMPLEMENTED;
+                GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, nbins, row_nnz, nullptr, Tm->csr.ptr, Tm->csr.idx, Tm->csr.val, err));
+                info = i3;
+            }
+        }
     }
-    dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(sbins.rows); dev_free(nbins.rows);
+    if (nvals_out) *nvals_out = (uint64_t)total;
+    dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(fbins.rows); dev_free(nbins.rows);
+    dev_free(Sp); dev_free(Sj); dev_free(Sx);
     if (info || symbolic_only) {
         if (Tm) GrB_Matrix_free(&Tm);
         return info;
