@@ -134,17 +134,18 @@ def cpu_mxm_sample(indptr, indices, values, n, budget_s=15.0, seed=0):
         idx = np.repeat(A.indptr[rows] - ptr[:-1], lens) + np.arange(ptr[-1])
         return R.BigMat(ptr, A.indices[idx], A.values[idx], rows.size, n)
 
-    probe_rows = rng.choice(n, size=min(n, 4096), replace=False)
-    t0 = time.perf_counter()
-    T = R.mxm_T("plus_times", sub(probe_rows), A)
-    t_probe = time.perf_counter() - t0
-    per_row = max(t_probe / probe_rows.size, 1e-9)
-    m = int(min(n, max(4096, budget_s / per_row)))
-    rows = rng.choice(n, size=m, replace=False)
-    As = sub(rows)
-    t0 = time.perf_counter()
-    T = R.mxm_T("plus_times", As, A)
-    dt = time.perf_counter() - t0
+    # grow the sample until it costs a meaningful fraction of the budget (per-call set-up of the dense accumulators --
+    # O(threads x ncols) -- would otherwise dominate a small sample and understate the CPU)
+    m = min(n, 1 << 15)
+    while True:
+        rows = rng.choice(n, size=m, replace=False)
+        As = sub(rows)
+        t0 = time.perf_counter()
+        T = R.mxm_T("plus_times", As, A)
+        dt = time.perf_counter() - t0
+        if dt >= budget_s / 3 or m >= n:
+            break
+        m = int(min(n, max(m * 2, m * (budget_s / max(dt, 1e-3)) * 0.7)))
     return T.nvals / dt, f"{m} random rows of A (of {n}) times full A, {T.nvals} output entries in {dt:.2f} s", R.num_threads()
 
 
@@ -372,7 +373,7 @@ def run_ours(args):
             y = M.mxv(xv, sr).new()
             if world == 1:
                 return y
-            yv, _ = gb.cuda.vector_as_torch(y)
+            yv, _ = gb.cuda.vector_as_torch(y, sync=False)   # same stream as torch
             pad = torch.zeros(rows_per, dtype=torch.float32, device=dev)
             pad[: q1 - q0] = yv
             dist.all_gather_into_tensor(gathered, pad)

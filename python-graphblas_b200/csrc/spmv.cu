@@ -19,7 +19,8 @@
 
 constexpr int SPMV_BLOCK = 256;
 
-template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? 6 : 8); };
+// items per thread: odd, so that the per-thread walk over shared memory (stride IPT words) is bank-conflict free
+template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? 5 : 7); };
 
 // ---- shuffle helpers for arbitrary 1..8 byte value types ----
 template <typename T> __device__ __forceinline__ T shfl_up_any(T v, int delta) {
@@ -152,11 +153,12 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
     unsigned emit_mask = 0, emit_has = 0;
     T acc = sr.identity();
     int has = 0;
+    int row_end = s_rowend[xr];   // re-read only when the row advances
 #pragma unroll
     for (int it = 0; it < IPT; it++) {
         emit_val[it] = acc;
         if (d + it < tile_items) {
-            if (yk < s_rowend[xr]) {
+            if (yk < row_end) {
                 bool ph = XFULL ? true : (s_has[yk] != 0);
                 if (ph) {
                     acc = has ? sr.add(acc, s_prod[yk]) : s_prod[yk];
@@ -168,6 +170,7 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
                 emit_mask |= 1u << it;
                 emit_has |= (unsigned)has << it;
                 xr++;
+                row_end = s_rowend[xr];
                 acc = sr.identity();
                 has = 0;
             }
@@ -384,7 +387,7 @@ static GrB_Info ensure_tiles(CsrArrays &c, int64_t nrows, int64_t nnz, int tile_
 }
 
 template <typename SR, typename T>
-static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz, const T *avals, const T *x,
+static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz, const T *avals, const T *x, int64_t x_len,
                          const uint8_t *xp, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
                          uint8_t *t_present, std::string *err) {
     if (mrows == 0) return GrB_SUCCESS;
@@ -506,7 +509,7 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
                 info = run_push<SRT, T>(sr, A->csr, A->nrows, a.out_len, (const T *)av, (const T *)uv, u->present,
                                         u->nvals, kflip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
             else
-                info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, up, kflip, a.mask,
+                info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, u->n, up, kflip, a.mask,
                                         a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
         }
         dev_free(atmp);

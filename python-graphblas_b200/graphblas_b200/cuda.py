@@ -161,9 +161,14 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
-def vector_as_torch(v):
-    """zero-copy torch views (values, present) of the vector's device arrays; call vector_touch(v) after writing."""
+def vector_as_torch(v, sync=True):
+    """zero-copy torch views (values, present) of the vector's device arrays; call vector_touch(v) after writing.
+    The library enqueues work on its own stream: unless torch shares that stream (use_torch_stream), the views are
+    only safe to read after a synchronisation, which `sync=True` performs."""
     import torch
+
+    if sync:
+        globals()["sync"]()
 
     pv, pp = vector_device_pointers(v)
     n = v.size

@@ -1,0 +1,155 @@
+"""Full-size (BASELINE.json scale-22) checks through size-independent properties -- the oracle cannot run these sizes
+in seconds, so the CUDA path is checked against identities that any correct implementation must satisfy:
+  * mxv with all-ones operands reproduces the degree vector exactly; merge-path and warp-per-row kernels agree bit-exactly;
+  * mxm: nvals equals the symbolic count, flops equals sum_k deg_A_col(k)*deg_B_row(k), and the checksum of checksums
+    C.1 == A.(A.1) holds exactly for small-integer values;
+  * BFS levels / SSSP distances satisfy the edge-relaxation optimality conditions on every edge.
+torch is used only to generate inputs on the device and to evaluate the properties."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCALE = 22
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import graphblas_b200 as gb
+
+    gb.init()
+    return gb
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def _rmat(torch, params, seed=42):
+    import bench
+
+    return bench.rmat_csr_torch(SCALE, params, seed, device=torch.device("cuda", 0))
+
+
+def _vec_to_torch(gb, torch, v):
+    vals, pres = gb.cuda.vector_as_torch(v)
+    return vals.clone(), pres.clone()
+
+
+def test_mxv_degree_identities(gb, torch):
+    import bench
+
+    ip, c, n = _rmat(torch, bench.RMAT_2B)
+    deg = (ip[1:] - ip[:-1])
+    ones = torch.ones(c.numel(), dtype=torch.float32, device=c.device)
+    A = gb.cuda.matrix_from_device_csr(ip, c, ones, n, n)
+    x = gb.cuda.vector_from_torch(torch.ones(n, dtype=torch.float32, device=c.device))
+    results = {}
+    for method in ("merge", "rowwarp"):
+        gb.cuda.set_option("spmv", method)
+        y = A.mxv(x, gb.semiring.plus_times).new()
+        vals, pres = _vec_to_torch(gb, torch, y)
+        assert torch.equal(pres.bool(), deg > 0)
+        assert torch.equal(vals[deg > 0], deg[deg > 0].to(torch.float32))      # max degree 97k < 2^24: exact in fp32
+        assert y.nvals == int((deg > 0).sum())
+        results[method] = vals
+        z = A.mxv(x, gb.semiring.any_pair).new()
+        zv, zp = _vec_to_torch(gb, torch, z)
+        assert torch.equal(zp.bool(), deg > 0) and bool((zv[deg > 0] == 1).all())
+    gb.cuda.set_option("spmv", "auto")
+    # int64 min_plus with x = 0: y(i) = min weight of row i; compare with a torch segmented min; both kernels bit-exact
+    g = torch.Generator(device=c.device); g.manual_seed(7)
+    w = torch.randint(1, 256, (c.numel(),), device=c.device, generator=g, dtype=torch.int64)
+    W = gb.cuda.matrix_from_device_csr(ip, c, w, n, n)
+    x0 = gb.cuda.vector_from_torch(torch.zeros(n, dtype=torch.int64, device=c.device))
+    rows = torch.repeat_interleave(torch.arange(n, device=c.device), deg)
+    want = torch.full((n,), 1 << 62, dtype=torch.int64, device=c.device).scatter_reduce(0, rows, w, "amin")
+    for method in ("merge", "rowwarp"):
+        gb.cuda.set_option("spmv", method)
+        y = W.mxv(x0, gb.semiring.min_plus).new()
+        vals, pres = _vec_to_torch(gb, torch, y)
+        assert torch.equal(vals[deg > 0], want[deg > 0]), method
+    gb.cuda.set_option("spmv", "auto")
+    # pull over the cached transpose == push: vxm(x, A) column sums == in-degree
+    indeg = torch.bincount(c.long(), minlength=n)
+    for vm in ("pull", "push"):
+        gb.cuda.set_option("vxm_method", vm)
+        y = x.vxm(A, gb.semiring.plus_times).new()
+        vals, pres = _vec_to_torch(gb, torch, y)
+        assert torch.equal(pres.bool(), indeg > 0), vm
+        assert torch.equal(vals[indeg > 0], indeg[indeg > 0].to(torch.float32)), vm
+    gb.cuda.set_option("vxm_method", "auto")
+
+
+def test_mxm_checksum_of_checksums(gb, torch):
+    import bench
+
+    ip, c, n = _rmat(torch, bench.RMAT_2A)
+    g = torch.Generator(device=c.device); g.manual_seed(11)
+    v = torch.randint(1, 3, (c.numel(),), device=c.device, generator=g, dtype=torch.int32)
+    A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
+    deg = (ip[1:] - ip[:-1])
+    flops_want = int(deg[c.long()].sum())
+    flops, nvals_sym = gb.cuda.mxm_symbolic(A, A)
+    assert flops == flops_want
+    C = A.mxm(A, gb.semiring.plus_times).new()
+    assert C.nvals == nvals_sym                       # one-pass numeric count == independent symbolic (two-pass) count
+    assert (C.nrows, C.ncols) == (n, n)
+    ones = gb.cuda.vector_from_torch(torch.ones(n, dtype=torch.int32, device=c.device))
+    lhs = C.mxv(ones, gb.semiring.plus_times).new()                                  # C.1 on the (unsorted) result
+    rhs = A.mxv(A.mxv(ones, gb.semiring.plus_times).new(), gb.semiring.plus_times).new()   # A.(A.1)
+    lv, lp = _vec_to_torch(gb, torch, lhs)
+    rv, rp = _vec_to_torch(gb, torch, rhs)
+    assert torch.equal(lp, rp) and torch.equal(lv[lp.bool()], rv[rp.bool()])
+    # structure-only product agrees on the pattern size
+    Cb = A.mxm(A, gb.semiring.any_pair).new()
+    assert Cb.nvals == C.nvals
+
+
+def test_bfs_and_sssp_optimality_conditions(gb, torch):
+    import bench
+
+    ip, c, n = _rmat(torch, bench.RMAT_2B)
+    deg = (ip[1:] - ip[:-1])
+    dev = c.device
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+    cols = c.long()
+    src = int(torch.nonzero(deg > 0)[0])
+    A = gb.cuda.matrix_from_device_csr(ip, c, torch.ones(c.numel(), dtype=torch.bool, device=dev), n, n)
+    # level BFS exactly as the reference notebook writes it
+    q = gb.Vector.from_coo([src], [True], size=n)
+    lv = gb.Vector(gb.dtypes.INT64, n)
+    for level in range(1, 200):
+        lv(mask=q.V)[:] = level
+        q(~lv.S, replace=True) << q.vxm(A, gb.semiring.any_pair)
+        if q.nvals == 0:
+            break
+    L, P = _vec_to_torch(gb, torch, lv)
+    P = P.bool()
+    assert bool(P[src]) and int(L[src]) == 1 and int(P.sum()) > n // 4
+    INF = 1 << 40
+    Lf = torch.where(P, L, torch.full_like(L, INF))
+    assert bool((Lf[cols] <= Lf[rows] + 1)[P[rows]].all())                 # no edge skips a level; reached set is closed
+    best = torch.full((n,), INF, dtype=torch.int64, device=dev).scatter_reduce(0, cols, Lf[rows], "amin")
+    reached = P.clone(); reached[src] = False
+    assert torch.equal(best[reached] + 1, L[reached])                       # every reached vertex has a parent one level up
+    # SSSP: Bellman-Ford sweeps w(min) << w.vxm(A, min_plus) to a fixed point
+    g = torch.Generator(device=dev); g.manual_seed(43)
+    w = torch.randint(1, 256, (c.numel(),), device=dev, generator=g, dtype=torch.int64)
+    W = gb.cuda.matrix_from_device_csr(ip, c, w, n, n)
+    d = gb.Vector.from_coo([src], [0], size=n, dtype=gb.dtypes.INT64)
+    for it in range(200):
+        old = d.dup()
+        d(gb.binary.min) << d.vxm(W, gb.semiring.min_plus)
+        if d.isequal(old):
+            break
+    D, DP = _vec_to_torch(gb, torch, d)
+    DP = DP.bool()
+    assert torch.equal(DP, P)                                                # same reachable set as BFS
+    Df = torch.where(DP, D, torch.full_like(D, INF))
+    assert bool((Df[cols] <= Df[rows] + w)[DP[rows]].all())                 # no edge can be relaxed further
+    bestd = torch.full((n,), INF, dtype=torch.int64, device=dev).scatter_reduce(0, cols, Df[rows] + w, "amin")
+    assert torch.equal(bestd[reached], D[reached]) and int(D[src]) == 0      # every distance is realised by an in-edge
