@@ -183,6 +183,100 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+def run_workloads(gb, torch, dev, scale):
+    """Level BFS (any_pair, complemented structural mask + replace), SSSP (min_plus, min accum, int64) and PageRank
+    (plus_second on A.T, fp64) on the Graph500-skew R-MAT, written exactly like the reference notebooks.
+    Device-resident; times are CUDA-event times of the whole loop, including the O(n) vector ops around the multiply."""
+    ip, c, n = rmat_csr_torch(scale, RMAT_2B, 42, device=dev)
+    nnz = c.numel()
+    deg = ip[1:] - ip[:-1]
+    src = int(torch.nonzero(deg > 0)[0])
+    out = {"graph": f"R-MAT scale-{scale} (0.57,0.19,0.19,0.05) ef16 seed42", "n": n, "nnz": nnz}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- BFS
+    A = gb.cuda.matrix_from_device_csr(ip, c, torch.ones(nnz, dtype=torch.bool, device=dev), n, n)
+    gb.cuda.matrix_build_transpose(A)
+
+    def bfs():
+        q = gb.Vector.from_coo([src], [True], size=n)
+        v = gb.Vector(gb.dtypes.INT64, n)
+        levels = 0
+        for level in range(1, n):
+            v(mask=q.V)[:] = level
+            q(~v.S, replace=True) << q.vxm(A, gb.semiring.any_pair)
+            levels = level
+            if q.nvals == 0:
+                break
+        return v, levels
+
+    v, levels = bfs()
+    torch.cuda.synchronize()
+    ev0.record()
+    v, levels = bfs()
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    vv, vp = gb.cuda.vector_as_torch(v, sync=False)
+    edges = int(deg[vp.bool()].sum())
+    out["bfs"] = {"ms": ms, "levels": levels, "reached": int(vp.sum()), "edges_traversed": edges, "GTEPS": edges / ms / 1e6}
+    del A
+
+    # ---- SSSP (Bellman-Ford sweeps to a fixed point, capped)
+    g = torch.Generator(device=dev); g.manual_seed(43)
+    w = torch.randint(1, 256, (nnz,), device=dev, generator=g, dtype=torch.int64)
+    W = gb.cuda.matrix_from_device_csr(ip, c, w, n, n)
+    gb.cuda.matrix_build_transpose(W)
+
+    def sssp():
+        d = gb.Vector.from_coo([src], [0], size=n, dtype=gb.dtypes.INT64)
+        its = 0
+        for it in range(64):
+            old = d.dup()
+            d(gb.binary.min) << d.vxm(W, gb.semiring.min_plus)
+            its += 1
+            if d.isequal(old):
+                break
+        return d, its
+
+    d, its = sssp()
+    torch.cuda.synchronize()
+    ev0.record()
+    d, its = sssp()
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    out["sssp"] = {"ms": ms, "iterations": its, "ms_per_iteration": ms / its, "reached": d.nvals,
+                   "mxv_algorithmic_GB_per_iteration": (nnz * 12 + (n + 1) * 8 + n * 8 * 3) / 1e9}
+    del W
+
+    # ---- PageRank: 20 iterations of the notebook recurrence, fp64
+    Af = gb.cuda.matrix_from_device_csr(ip, c, torch.ones(nnz, dtype=torch.float64, device=dev), n, n)
+    gb.cuda.matrix_build_transpose(Af)
+    dvec = gb.cuda.vector_from_torch(torch.clamp(deg, min=1).to(torch.float64))
+    damping, teleport = 0.85, (1 - 0.85) / n
+
+    def pagerank(iters):
+        t = gb.cuda.vector_from_torch(torch.full((n,), 1.0 / n, dtype=torch.float64, device=dev))
+        for _ in range(iters):
+            wv = t.ewise_mult(dvec, gb.binary.truediv).new()
+            wv = wv.apply(gb.binary.times, right=damping).new()
+            r = gb.Vector(gb.dtypes.FP64, n)
+            r[:] = teleport
+            r(gb.binary.plus) << Af.T.mxv(wv, gb.semiring.plus_second)
+            t = r
+        return t
+
+    t = pagerank(2)
+    torch.cuda.synchronize()
+    ev0.record()
+    t = pagerank(20)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    out["pagerank"] = {"ms": ms, "iterations": 20, "ms_per_iteration": ms / 20, "sum": t.reduce(gb.monoid.plus).value,
+                       "mxv_algorithmic_GB_per_iteration": (nnz * 4 + (n + 1) * 8 + n * 8 + n * 9 * 2) / 1e9}
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -404,6 +498,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---------------- the iterative workloads of BASELINE.json configs 3-5 as the reference notebooks write them (N == 1)
+    workloads = None
+    if world == 1 and not args.no_workloads:
+        try:
+            workloads = run_workloads(gb, torch, dev, scale)
+        except Exception as exc:
+            workloads = {"error": repr(exc)}
+
     # ---------------- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -427,7 +529,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "spgemm_numeric_*", "achieved": roof_ach, "peak": hbm, "unit": "GB/s",
                      "frac": (roof_ach / hbm) if roof_ach else None, "peak_source": pk_kind, "traffic": None,
                      "algorithmic_bytes": int(numeric_bytes), "bmin_frac_whole_step": bmin_bytes / (ms_dev * 1e-3) / 1e9 / hbm},
-        "e2e": e2e, "mxv": mxv, "cpu_baseline": cpu,
+        "e2e": e2e, "mxv": mxv, "workloads": workloads, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
@@ -444,6 +546,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mxv", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

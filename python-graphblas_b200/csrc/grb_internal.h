@@ -81,6 +81,9 @@ void set_last_error(const char *msg);
 GrB_Info cuda_fail(std::string *slot, cudaError_t e, const char *what);
 void *dev_alloc(size_t bytes);             // stream-ordered; returns nullptr on failure (error recorded)
 void dev_free(void *p);
+void *ws_acquire(int slot, size_t bytes);   // cached scratch (see runtime.cu)
+void ws_release(int slot, void *p);
+void ws_trim();
 template <typename T> static inline T *dev_alloc_t(size_t n) { return (T *)dev_alloc(n * sizeof(T)); }
 const char *opt_get(const char *key, const char *dflt);
 long opt_get_int(const char *key, long dflt);

@@ -145,6 +145,29 @@ void dev_free(void *p) {
 
 extern "C" size_t GrB_cuda_memory_in_use(void) { return g_bytes_in_use; }
 
+// Workspace slots: large scratch buffers that recur with the same size on every call of an iterative workload
+// (SpGEMM staging).  Kept across calls so the steady state performs no allocator work at all; dropped by
+// GrB_cuda_set_option("trim", "1") / GrB_finalize or when a request no longer fits the cached block.
+static struct { void *ptr; size_t bytes; bool busy; } g_ws[8];
+void *ws_acquire(int slot, size_t bytes) {
+    auto &w = g_ws[slot];
+    if (w.ptr && !w.busy && w.bytes >= bytes && w.bytes <= bytes + bytes / 2 + (1 << 20)) { w.busy = true; return w.ptr; }
+    if (w.ptr && !w.busy) { dev_free(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+    if (w.busy) return dev_alloc(bytes);   // nested use: plain allocation (released by ws_release via pointer check)
+    void *p = dev_alloc(bytes);
+    if (p) { w.ptr = p; w.bytes = bytes; w.busy = true; }
+    return p;
+}
+void ws_release(int slot, void *p) {
+    auto &w = g_ws[slot];
+    if (p && p == w.ptr) { w.busy = false; return; }
+    dev_free(p);
+}
+void ws_trim() {
+    for (auto &w : g_ws)
+        if (w.ptr && !w.busy) { dev_free(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+}
+
 const char *opt_get(const char *key, const char *dflt) {
     auto it = g_opts.find(key);
     if (it != g_opts.end()) return it->second.c_str();
@@ -163,6 +186,7 @@ extern "C" GrB_Info GrB_cuda_set_option(const char *key, const char *value) {
     if (!value) g_opts.erase(key);
     else g_opts[key] = value;
     if (!strcmp(key, "profile")) g_profile = value && atoi(value) != 0;
+    if (!strcmp(key, "trim")) ws_trim();
     return GrB_SUCCESS;
 }
 extern "C" const char *GrB_cuda_get_option(const char *key) { return key ? opt_get(key, "") : ""; }
@@ -211,6 +235,7 @@ extern "C" GrB_Info GrB_init(GrB_Mode mode) {
 
 extern "C" GrB_Info GrB_finalize(void) {
     if (!g_initialized) return GrB_SUCCESS;
+    ws_trim();
     cudaStreamSynchronize(g_stream);
     g_initialized = false;
     return GrB_SUCCESS;

@@ -28,7 +28,7 @@
 constexpr int HASH_EMPTY = -1;
 constexpr unsigned long long HASH_EMPTY64 = ~0ull;
 constexpr int LPE = 8;    // lanes per A entry in the warp-per-row kernel
-constexpr int MAX_THREADS = 512;
+constexpr int MAX_THREADS = 1024;
 
 __device__ __forceinline__ unsigned hash_slot(int key, unsigned size) {
     return (unsigned)(((unsigned long long)((unsigned)key * 0x9E3779B1u) * size) >> 32);   // multiply-shift into [0, size)
@@ -158,8 +158,8 @@ struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; in
 static BinSpec make_bin_spec(size_t entry_bytes) {
     BinSpec s;
     const int caps[NBINS] = {0, 64, 256, 512, 1024, 2048, 4096, 8192, 16384, 0, 0};
-    const int thr[NBINS] = {0, 256, 256, 128, 128, 256, 256, 256, 512, 512, 512};
-    int maxcap = (int)((212 * 1024) / entry_bytes);   // 227 KB minus the kernel's static arrays
+    const int thr[NBINS] = {0, 256, 256, 128, 128, 256, 256, 512, 1024, 1024, 1024};   // big tables: more warps per CTA, occupancy is smem-bound
+    int maxcap = (int)((204 * 1024) / entry_bytes);   // 227 KB minus the kernel's static arrays (chunk staging for 1024 threads)
     maxcap -= maxcap % 256;
     for (int b = 0; b < NBINS; b++) { s.cap[b] = caps[b]; s.threads[b] = thr[b]; }
     s.cap[9] = maxcap > 16384 + 2048 ? maxcap : 16384;
@@ -494,7 +494,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
         } else if (b < NBINS - 1) {
             const size_t smem = (size_t)cap * entry;
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
-            if (smem > 32 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));   // static + dynamic may exceed 48 KB in any bin
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
             kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr);
         } else {
@@ -524,7 +524,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 if (!info) {
                     cudaMemcpyAsync(doffs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, g_stream);
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 512, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs);
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs);
                     cudaStreamSynchronize(g_stream);   // offs is host memory
                 }
                 dev_free(doffs); dev_free(gt);
@@ -661,8 +661,8 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         info = make_bins(&fbins, entry, p.m, flops, err);
         if (!info) {
             Sp = dev_alloc_t<int64_t>((size_t)p.m + 1);
-            Sj = dev_alloc_t<int32_t>((size_t)total_flops);
-            Sx = dev_alloc((size_t)total_flops * es);
+            Sj = (int32_t *)ws_acquire(0, (size_t)total_flops * 4);
+            Sx = ws_acquire(1, (size_t)total_flops * es);
             if (!Sp || !Sj || !Sx) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm staging (%llu products)", (unsigned long long)total_flops);
         }
         if (!info) {
@@ -735,7 +735,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     }
     if (nvals_out) *nvals_out = (uint64_t)total;
     dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(fbins.rows); dev_free(nbins.rows);
-    dev_free(Sp); dev_free(Sj); dev_free(Sx);
+    dev_free(Sp); ws_release(0, Sj); ws_release(1, Sx);
     if (info || symbolic_only) {
         if (Tm) GrB_Matrix_free(&Tm);
         return info;
