@@ -34,6 +34,28 @@ RMAT_2A = (0.45, 0.15, 0.15)   # mild skew: nnz(C) fits
 RMAT_2B = (0.57, 0.19, 0.19)   # Graph500
 
 
+def ncu_traffic():
+    """DRAM bytes per launch measured by ncu (profiles/traffic_r01.json, produced by scripts/summarize_profiles.py from the
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture of the same workload); None when absent."""
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic_r01.json").read_text())
+    except Exception:
+        return None, None
+    mxm = mxv = None
+    try:
+        rows = [v for k, v in t["mxm22"].items() if k.startswith(("spgemm_block_kernel", "spgemm_warp_kernel"))]
+        calls = 2   # the capture ran A.mxm(A) twice
+        mxm = sum(r["dram_MB"] for r in rows) * 1e6 / calls
+    except Exception:
+        pass
+    try:
+        r = [v for k, v in t["mxv22"].items() if k.startswith("spmv_merge_kernel")][0]
+        mxv = r["dram_MB"] * 1e6 / r["launches"]
+    except Exception:
+        pass
+    return mxm, mxv
+
+
 def peaks():
     try:
         return json.loads((ROOT / "MEASURED_PEAKS.json").read_text()), "measured"
@@ -460,18 +482,27 @@ def run_ours(args):
         M = gb.cuda.matrix_from_device_csr((ip2[q0:q1 + 1] - p0).contiguous(), c2[p0:p1].contiguous(), v2[p0:p1].contiguous(), q1 - q0, n2)
         x_t = values_torch(n2, 46, torch.float32, device=dev)
         x = gb.cuda.vector_from_torch(x_t)
-        gathered = torch.empty(rows_per * world, dtype=torch.float32, device=dev)
+        # the per-iteration exchange of the row-partitioned path: every rank's output slice is all-gathered straight into
+        # the device buffer of the next input vector (zero-copy torch views of the library's arrays; NCCL over NVLink)
+        x_next = gb.cuda.vector_from_torch(torch.zeros(n2, dtype=torch.float32, device=dev)) if world > 1 else None
+        xn_vals = gb.cuda.vector_as_torch(x_next, sync=False)[0] if world > 1 else None
+        zero_copy = world > 1 and n2 % world == 0
+        gathered = torch.empty(rows_per * world, dtype=torch.float32, device=dev) if (world > 1 and not zero_copy) else None
         iters = max(20, args.steps * 4)
 
         def mxv_iter(xv):
             y = M.mxv(xv, sr).new()
             if world == 1:
                 return y
-            yv, _ = gb.cuda.vector_as_torch(y, sync=False)   # same stream as torch
-            pad = torch.zeros(rows_per, dtype=torch.float32, device=dev)
-            pad[: q1 - q0] = yv
-            dist.all_gather_into_tensor(gathered, pad)
-            return gb.cuda.vector_from_torch(gathered[:n2])
+            yv, _ = gb.cuda.vector_as_torch(y, sync=False)   # same stream as torch: no synchronisation needed
+            if zero_copy:
+                dist.all_gather_into_tensor(xn_vals, yv)
+            else:
+                pad = torch.zeros(rows_per, dtype=torch.float32, device=dev)
+                pad[: q1 - q0] = yv
+                dist.all_gather_into_tensor(gathered, pad)
+                xn_vals.copy_(gathered[:n2])
+            return y
 
         y = None
         for _ in range(5):
@@ -490,7 +521,8 @@ def run_ours(args):
         mxv = {"workload": f"R-MAT scale-{scale} (0.57,0.19,0.19,0.05) plus_times fp32 A.mxv(x), x dense", "nnz": nnz2,
                "ms_per_iter": ms_mxv, "GB_per_s": gbs, "nnz_per_s": nnz2 / (ms_mxv * 1e-3),
                "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": hbm, "unit": "GB/s", "frac": gbs / world / hbm,
-                            "peak_source": pk_kind, "traffic": None}}
+                            "peak_source": pk_kind, "traffic": (ncu_traffic()[1] if (scale == 22 and world == 1) else None),
+                            "kernel": "spmv_merge_kernel (per-call time also covers fix-up kernel and host overhead)"}}
         del M
 
     if rank != 0:
@@ -527,7 +559,9 @@ def run_ours(args):
         "clocks": clk.summary(), "gpu_launches": launches_per_step,
         "phases_ms": {"symbolic": symbolic_ms, "numeric": numeric_ms, "sort_on_demand": sort_ms, "kernels": {k: v[0] for k, v in kt.items()}},
         "roofline": {"bound": "hbm", "kernel": "spgemm_numeric_*", "achieved": roof_ach, "peak": hbm, "unit": "GB/s",
-                     "frac": (roof_ach / hbm) if roof_ach else None, "peak_source": pk_kind, "traffic": None,
+                     "frac": (roof_ach / hbm) if roof_ach else None, "peak_source": pk_kind,
+                     "traffic": (ncu_traffic()[0] if (scale == 22 and world == 1) else None),
+                     "traffic_note": "ncu dram bytes of all numeric hash kernels of one A.mxm(A) (profiles/ncu_mxm22_r01.txt)",
                      "algorithmic_bytes": int(numeric_bytes), "bmin_frac_whole_step": bmin_bytes / (ms_dev * 1e-3) / 1e9 / hbm},
         "e2e": e2e, "mxv": mxv, "workloads": workloads, "cpu_baseline": cpu,
     }

@@ -19,6 +19,35 @@ static bool semiring_supported(const GrB_Semiring op) {
     }
 }
 
+
+// shared tail of GrB_mxv / GrB_vxm: multiply (with the write-back fused into the kernel when possible), then write back
+static GrB_Info mat_vec_common(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring op, GrB_Matrix A,
+                               bool use_transpose, GrB_Vector u, bool flip, const GrB_Descriptor desc) {
+    const bool comp = desc && desc->comp, structure = desc && desc->structure, replace = desc && desc->replace;
+    const uint8_t *mbytes = nullptr;
+    void *mtmp = nullptr;
+    if (mask) {
+        GRB_TRY(vector_ensure_arrays(mask));
+        GRB_TRY(mask_effective_bytes(&mbytes, &mtmp, mask->present, mask->vals, mask->type, mask->n, structure, &w->err));
+    }
+    const bool needs_epi = mask != nullptr || accum != nullptr || comp;
+    const bool can_fuse = needs_epi && w->type == op->type && (!accum || (accum->type == w->type && accum->ztype == accum->type)) &&
+                          opt_get_int("fuse_epilogue", 1) != 0;
+    VecEpiHost epi{w->vals, w->present, mbytes, mask != nullptr, comp, replace, accum ? accum->opcode : OP_NONE};
+    void *tv = nullptr;
+    uint8_t *tp = nullptr;
+    int64_t tl = 0;
+    bool fused = false;
+    GrB_Info info = multiply_mat_vec_impl(&tv, &tp, &tl, op, A, use_transpose, u, flip, mbytes, comp, &w->err, can_fuse ? &epi : nullptr, &fused);
+    dev_free(mtmp);
+    GRB_TRY(info);
+    if (fused) {
+        vector_take_arrays(w, tv, tp, -1);
+        return GrB_SUCCESS;
+    }
+    return vector_write_back(w, tv, tp, op->type, mask, accum, desc, true);
+}
+
 extern "C" GrB_Info GrB_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring op,
                             const GrB_Matrix A, const GrB_Vector u, const GrB_Descriptor desc) {
     CHECK_INIT();
@@ -31,20 +60,7 @@ extern "C" GrB_Info GrB_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_Binar
     if (w->n != out_len || u->n != in_len || (mask && mask->n != w->n))
         return set_error(&w->err, GrB_DIMENSION_MISMATCH, "GrB_mxv: w(%lld) = A(%lldx%lld%s) * u(%lld), mask(%lld)", (long long)w->n,
                          (long long)A->nrows, (long long)A->ncols, t0 ? ")'" : ")", (long long)u->n, (long long)(mask ? mask->n : w->n));
-    const bool comp = desc && desc->comp, structure = desc && desc->structure;
-    const uint8_t *mbytes = nullptr;
-    void *mtmp = nullptr;
-    if (mask) {
-        GRB_TRY(vector_ensure_arrays(mask));
-        GRB_TRY(mask_effective_bytes(&mbytes, &mtmp, mask->present, mask->vals, mask->type, mask->n, structure, &w->err));
-    }
-    void *tv = nullptr;
-    uint8_t *tp = nullptr;
-    int64_t tl = 0;
-    GrB_Info info = multiply_mat_vec_impl(&tv, &tp, &tl, op, A, t0, u, /*flip=*/false, mbytes, comp, &w->err);
-    dev_free(mtmp);
-    GRB_TRY(info);
-    return vector_write_back(w, tv, tp, op->type, mask, accum, desc, true);
+    return mat_vec_common(w, mask, accum, op, A, t0, u, /*flip=*/false, desc);
 }
 
 extern "C" GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring op,
@@ -60,20 +76,7 @@ extern "C" GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_Binar
     if (w->n != out_len || u->n != in_len || (mask && mask->n != w->n))
         return set_error(&w->err, GrB_DIMENSION_MISMATCH, "GrB_vxm: w(%lld) = u(%lld) * A(%lldx%lld%s, mask(%lld)", (long long)w->n,
                          (long long)u->n, (long long)A->nrows, (long long)A->ncols, t1 ? ")'" : ")", (long long)(mask ? mask->n : w->n));
-    const bool comp = desc && desc->comp, structure = desc && desc->structure;
-    const uint8_t *mbytes = nullptr;
-    void *mtmp = nullptr;
-    if (mask) {
-        GRB_TRY(vector_ensure_arrays(mask));
-        GRB_TRY(mask_effective_bytes(&mbytes, &mtmp, mask->present, mask->vals, mask->type, mask->n, structure, &w->err));
-    }
-    void *tv = nullptr;
-    uint8_t *tp = nullptr;
-    int64_t tl = 0;
-    GrB_Info info = multiply_mat_vec_impl(&tv, &tp, &tl, op, A, /*use_transpose=*/!t1, u, /*flip=*/true, mbytes, comp, &w->err);
-    dev_free(mtmp);
-    GRB_TRY(info);
-    return vector_write_back(w, tv, tp, op->type, mask, accum, desc, true);
+    return mat_vec_common(w, mask, accum, op, A, /*use_transpose=*/!t1, u, /*flip=*/true, desc);
 }
 
 extern "C" GrB_Info GrB_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Semiring op,

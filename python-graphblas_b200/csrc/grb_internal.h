@@ -140,9 +140,12 @@ GrB_Info matrix_write_back(GrB_Matrix C, GrB_Matrix T, const GrB_Matrix M, const
 // multiply cores
 // t = M (+).(x) u where M = A (use_transpose=false) or A' (true); flip: multiply is mul(u_k, a) instead of mul(a, u_k).
 // mask_eff (nullable): byte per output position, rows/positions ruled out by the mask may be skipped.
+// epi (nullable): write-back parameters; when the traversal can finish each output position exactly once (pull
+// kernels) it is applied inside the kernel and *fused is set -- the returned arrays are then the FINAL output.
+struct VecEpiHost { const void *c_vals; const uint8_t *c_present; const uint8_t *mask; int has_mask, comp, replace, accum; };
 GrB_Info multiply_mat_vec_impl(void **t_vals, uint8_t **t_present, int64_t *t_len, const GrB_Semiring op, GrB_Matrix A,
                                bool use_transpose, GrB_Vector u, bool flip, const uint8_t *mask_eff, bool mask_comp,
-                               std::string *err);
+                               std::string *err, const VecEpiHost *epi, bool *fused);
 GrB_Info spgemm(GrB_Matrix *T, const GrB_Semiring op, GrB_Matrix A, bool at, GrB_Matrix B, bool bt,
                 const GrB_Matrix M, bool mask_comp, bool mask_struct, std::string *err, bool symbolic_only,
                 uint64_t *flops_out, uint64_t *nvals_out);

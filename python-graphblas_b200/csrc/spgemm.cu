@@ -27,6 +27,7 @@
 
 constexpr int HASH_EMPTY = -1;
 constexpr unsigned long long HASH_EMPTY64 = ~0ull;
+constexpr int MASK_FLAG = (int)0x80000000;   // column indices are < 2^31 - 1, so bit 31 is free
 constexpr int LPE = 8;    // lanes per A entry in the warp-per-row kernel
 constexpr int MAX_THREADS = 1024;
 
@@ -107,19 +108,56 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
             }
         }
     }
+    // ---- masked product (C<M> = A*B, M not complemented): the row's table is pre-loaded with the mask row's columns,
+    // each tagged MASK_FLAG ("allowed, nothing accumulated yet").  A product whose column is not in the table is dropped
+    // before any arithmetic is stored; the first product that hits a column clears the tag (idempotent atomicAnd),
+    // values start at the monoid identity so every hit is just an atomic combine.
+    __device__ __forceinline__ void insert_mask(const SR &sr, int j) {
+        unsigned h = hash_slot(j, size);
+        if (kPacked) {
+            const unsigned long long mine = pack_entry<T>(j | MASK_FLAG, sr.identity());
+            while (true) {
+                unsigned long long cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
+                if (cur == HASH_EMPTY64 || ((int)(cur >> 32) & ~MASK_FLAG) == j) return;
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        } else {
+            while (true) {
+                int cur = atomicCAS(&keys[h], HASH_EMPTY, j | MASK_FLAG);
+                if (cur == HASH_EMPTY || (cur & ~MASK_FLAG) == j) return;
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        }
+    }
+    // returns 1 when this product is the first to land on its (allowed) column, 0 otherwise (incl. "not in the mask")
+    __device__ __forceinline__ int accumulate_masked(const SR &sr, int j, T p) {
+        unsigned h = hash_slot(j, size);
+        while (true) {
+            int *kp = kPacked ? reinterpret_cast<int *>(&ent[h]) + 1 : &keys[h];
+            const int cur = *kp;
+            if (cur == HASH_EMPTY) return 0;
+            if ((cur & ~MASK_FLAG) == j) {
+                int fresh = 0;
+                if (cur & MASK_FLAG) fresh = (atomicAnd(kp, ~MASK_FLAG) & MASK_FLAG) != 0;
+                if (NUMERIC) atomic_combine(sr, kPacked ? reinterpret_cast<T *>(&ent[h]) : &vals[h], p);
+                return fresh;
+            }
+            h = (h + 1 == size) ? 0 : h + 1;
+        }
+    }
     // copy every occupied slot to out[*count ...] (count is a shared-memory counter)
     __device__ __forceinline__ void drain(int tid, int nthreads, int *count, int32_t *__restrict__ oj, T *__restrict__ ox) {
         for (unsigned t = tid; t < size; t += nthreads) {
             if (kPacked) {
                 const unsigned long long e = ent[t];
-                if (e != HASH_EMPTY64) {
+                if ((int)(e >> 32) >= 0) {   // neither empty nor an untouched mask column
                     const int pos = atomicAdd(count, 1);
                     oj[pos] = (int)(e >> 32);
                     ox[pos] = unpack_value<T>(e);
                 }
             } else {
                 const int key = keys[t];
-                if (key != HASH_EMPTY) {
+                if (key >= 0) {
                     const int pos = atomicAdd(count, 1);
                     oj[pos] = key;
                     ox[pos] = vals[t];
@@ -214,13 +252,16 @@ __global__ void bin_fill_kernel(BinSpec spec, int64_t nrows, const int64_t *__re
     }
 }
 
+struct MaskArgs { const int64_t *Mp; const int32_t *Mj; const uint8_t *Meff; };   // Mp == nullptr: unmasked
+
 // ------------------------------------------------------------------ warp-per-row kernel (tiny rows)
 template <typename SR, typename T, bool NUMERIC, bool PACK>
 __global__ void __launch_bounds__(256)
 spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
                    const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
                    const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
-                   int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox) {
+                   int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox,
+                   MaskArgs mk) {
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane32 = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -236,6 +277,11 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
     if (active) tab.init(sr, lane32, 32);
     if (lane32 == 0) *count = 0;
     __syncwarp();
+    if (active && mk.Mp) {
+        for (int64_t k = mk.Mp[row] + lane32; k < mk.Mp[row + 1]; k += 32)
+            if (!mk.Meff || mk.Meff[k]) tab.insert_mask(sr, mk.Mj[k]);
+    }
+    __syncwarp();
     int local_new = 0;
     if (active) {
         const int sub = lane32 / LPE, lane = lane32 % LPE;
@@ -249,7 +295,7 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
                 const int j = Bj[q];
                 T p = T();
                 if (NUMERIC) p = sr.mul(a, sr.reads_b() ? Bx[q] : one_of<T>());
-                local_new += tab.insert(sr, j, p);
+                local_new += mk.Mp ? tab.accumulate_masked(sr, j, p) : tab.insert(sr, j, p);
             }
         }
     }
@@ -279,7 +325,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
                                     const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
                                     const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
                                     int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
-                                    T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets) {
+                                    T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets, MaskArgs mk) {
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int64_t s_bs[MAX_THREADS];
@@ -303,6 +349,11 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
     }
     tab.init(sr, tid, nthreads);
     if (tid == 0) s_count = 0;
+    if (mk.Mp) {
+        __syncthreads();
+        for (int64_t k = mk.Mp[row] + tid; k < mk.Mp[row + 1]; k += nthreads)
+            if (!mk.Meff || mk.Meff[k]) tab.insert_mask(sr, mk.Mj[k]);
+    }
 
     const int wlane = tid & 31, warp = tid >> 5;
     const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
@@ -357,7 +408,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
                 if (jj[u] == HASH_EMPTY) continue;
                 T pr = T();
                 if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                local_new += tab.insert(sr, jj[u], pr);
+                local_new += mk.Mp ? tab.accumulate_masked(sr, jj[u], pr) : tab.insert(sr, jj[u], pr);
             }
         }
         __syncthreads();   // s_* arrays are rewritten by the next chunk
@@ -401,6 +452,18 @@ __global__ void reduce_sum_max_kernel(const int64_t *__restrict__ v, int64_t n, 
         mx = om > mx ? om : mx;
     }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); }
+}
+// masked product: the table holds the mask row, the work is the row's flops; bin by whichever asks for the bigger CTA
+__global__ void masked_count_kernel(int64_t nrows, const int64_t *__restrict__ flops, const int64_t *__restrict__ Mp,
+                                    int64_t work_cap, int64_t *__restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nrows; i += s) {
+        const int64_t mn = Mp[i + 1] - Mp[i], f = flops[i];
+        int64_t w = f >> 5;
+        if (w > work_cap) w = work_cap;
+        cnt[i] = (mn > 0 && f > 0) ? (mn > w ? mn : w) : 0;
+    }
 }
 // staging (addressed by the flops prefix) -> final CSR: one warp per row, coalesced both ways, 4 loads in flight
 template <typename T>
@@ -471,6 +534,7 @@ struct HashArgs {
     int64_t *row_nnz;                  // written when non-null (symbolic count, or exact count of a one-pass row)
     const int64_t *Op; int32_t *Oj; void *Ox;   // numeric output: row i's entries go to O*[Op[i] ...]
     const int64_t *cnt;                // per-row bound the bins / table sizes were derived from
+    MaskArgs mk;                       // mask row pattern (Mp == nullptr: unmasked)
 };
 
 template <typename SR, typename T, bool NUMERIC, bool PACK>
@@ -490,13 +554,13 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             auto kern = spgemm_warp_kernel<SR, T, NUMERIC, PACK>;
             if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
-            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
         } else if (b < NBINS - 1) {
             const size_t smem = (size_t)cap * entry;
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
             CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));   // static + dynamic may exceed 48 KB in any bin
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
-            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr);
+            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
@@ -524,7 +588,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 if (!info) {
                     cudaMemcpyAsync(doffs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, g_stream);
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs);
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
                     cudaStreamSynchronize(g_stream);   // offs is host memory
                 }
                 dev_free(doffs); dev_free(gt);
@@ -552,7 +616,7 @@ template <typename T> static size_t numeric_entry_bytes() { return (Packed<T>::v
 // numeric pass writing row i at O*[Op[i]...]; row_nnz (optional) receives exact counts
 template <typename T>
 static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p, const Bins &bins, const int64_t *cnt,
-                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, std::string *err) {
+                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, MaskArgs mk, std::string *err) {
     GrB_Info info = GrB_SUCCESS;
     const int T_code = type_code_of<T>();
     GRB_DISPATCH_SEMIRING(op->add, op->mul, T, SRT, sr, {
@@ -561,7 +625,7 @@ static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p,
         if (sr.reads_a()) info = cast_view(&ax, &atmp, p.A->val, p.a_type, T_code, p.annz, err);
         if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
         if (!info) {
-            HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt};
+            HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt, mk};
             if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
             else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
         }
@@ -581,7 +645,6 @@ static void launch_compact(int64_t m, const int64_t *Sp, const int64_t *Cp, cons
 GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, GrB_Matrix B, bool bt, const GrB_Matrix M,
                 bool mask_comp, bool mask_struct, std::string *err, bool symbolic_only, uint64_t *flops_out,
                 uint64_t *nvals_out) {
-    (void)M; (void)mask_comp; (void)mask_struct;   // the write-back applies the mask; see DESIGN.md
     GRB_TRY(matrix_materialize(A));
     GRB_TRY(matrix_materialize(B));
     if (at) GRB_TRY(matrix_ensure_twin(A));
@@ -654,7 +717,65 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     int64_t total = 0;
     const unsigned copy_blocks = (unsigned)std::min<int64_t>((p.m + 256) / 256, (int64_t)g_num_sms * 8);
 
-    if (!info && onepass) {
+    const bool masked = M && !mask_comp && !symbolic_only && total_flops > 0 && opt_get_int("spgemm_mask", 1) != 0;
+    if (!info && masked) {
+        // ---- C<M> = A*B, M not complemented: hash tables pre-loaded with the mask rows; output bounded by nnz(M),
+        //      so the staging CSR simply has M's row pointers and no symbolic pass is needed
+        GrB_Info im = matrix_materialize(M);
+        const uint8_t *meff = nullptr;
+        void *mtmp = nullptr;
+        if (!im && !mask_struct && M->nvals > 0) im = mask_effective_bytes(&meff, &mtmp, nullptr, M->csr.val, M->type, M->nvals, false, err);
+        info = im;
+        size_t entry = 12;
+        GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
+        int64_t *mcnt = dev_alloc_t<int64_t>((size_t)p.m + 1);
+        int32_t *Mj_stage = nullptr;
+        void *Mx_stage = nullptr;
+        if (!info && !mcnt) info = set_error(err, GrB_OUT_OF_MEMORY, "masked spgemm counts");
+        if (!info) {
+            BinSpec spec = make_bin_spec(entry);
+            note_launch("masked_count");
+            masked_count_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, M->csr.ptr, spec.maxcount[9], mcnt);
+            info = make_bins(&fbins, entry, p.m, mcnt, err);
+        }
+        if (!info) {
+            const size_t cap = (size_t)(M->nvals > 0 ? M->nvals : 1);
+            Mj_stage = dev_alloc_t<int32_t>(cap);
+            Mx_stage = dev_alloc(cap * es);
+            if (!Mj_stage || !Mx_stage) info = set_error(err, GrB_OUT_OF_MEMORY, "masked spgemm staging");
+        }
+        if (!info) {
+            GrB_Info i3 = GrB_NOT_IMPLEMENTED;
+            MaskArgs mk{M->csr.ptr, M->csr.idx, meff};
+            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, mcnt, row_nnz, M->csr.ptr, Mj_stage, Mx_stage, mk, err));
+            info = i3;
+        }
+        if (!info) {
+            note_launch("i64_copy");
+            i64_copy_kernel<<<copy_blocks, 256, 0, g_stream>>>(Tm->csr.ptr, row_nnz, p.m + 1);
+            info = exclusive_scan_i64(Tm->csr.ptr, p.m + 1, err);
+            if (!info) total = read_i64(Tm->csr.ptr + p.m);
+        }
+        if (!info) {
+            size_t nv = (size_t)(total > 0 ? total : 1);
+            Tm->csr.idx = dev_alloc_t<int32_t>(nv);
+            Tm->csr.val = dev_alloc(nv * es);
+            Tm->nvals = total;
+            Tm->jumbled = true;
+            if (!Tm->csr.idx || !Tm->csr.val) info = set_error(err, GrB_OUT_OF_MEMORY, "masked mxm result");
+        }
+        if (!info && total > 0) {
+            switch (es) {
+                case 1: launch_compact<uint8_t>(p.m, M->csr.ptr, Tm->csr.ptr, Mj_stage, Mx_stage, Tm->csr.idx, Tm->csr.val); break;
+                case 2: launch_compact<uint16_t>(p.m, M->csr.ptr, Tm->csr.ptr, Mj_stage, Mx_stage, Tm->csr.idx, Tm->csr.val); break;
+                case 4: launch_compact<uint32_t>(p.m, M->csr.ptr, Tm->csr.ptr, Mj_stage, Mx_stage, Tm->csr.idx, Tm->csr.val); break;
+                default: launch_compact<uint64_t>(p.m, M->csr.ptr, Tm->csr.ptr, Mj_stage, Mx_stage, Tm->csr.idx, Tm->csr.val); break;
+            }
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) info = cuda_fail(err, e, "masked spgemm compaction");
+        }
+        dev_free(mtmp); dev_free(mcnt); dev_free(Mj_stage); dev_free(Mx_stage);
+    } else if (!info && onepass) {
         // ---- bins and tables from the flops bound; staging addressed by the flops prefix
         size_t entry = 12;
         GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
@@ -672,7 +793,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         }
         if (!info) {
             GrB_Info i3 = GrB_NOT_IMPLEMENTED;
-            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, flops, row_nnz, Sp, Sj, Sx, err));
+            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, flops, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err));
             info = i3;
         }
         if (!info) {
@@ -704,7 +825,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         if (p.m > 0 && total_flops > 0) {
             info = make_bins(&fbins, 4, p.m, flops, err);
             if (!info) {
-                HashArgs a{p.A->ptr, p.A->idx, nullptr, p.B->ptr, p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops};
+                HashArgs a{p.A->ptr, p.A->idx, nullptr, p.B->ptr, p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops, MaskArgs{nullptr, nullptr, nullptr}};
                 SRDyn<int32_t> dummy;
                 dummy.a_op = OP_ANY; dummy.m_op = OP_PAIR;
                 info = run_bins<SRDyn<int32_t>, int32_t, false, false>(dummy, fbins, a, err);
@@ -728,7 +849,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             if (!info && total > 0) info = make_bins(&nbins, entry, p.m, row_nnz, err);
             if (!info && total > 0) {
                 GrB_Info i3 = GrB_NOT_IMPLEMENTED;
-                GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, nbins, row_nnz, nullptr, Tm->csr.ptr, Tm->csr.idx, Tm->csr.val, err));
+                GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, nbins, row_nnz, nullptr, Tm->csr.ptr, Tm->csr.idx, Tm->csr.val, MaskArgs{nullptr, nullptr, nullptr}, err));
                 info = i3;
             }
         }

@@ -66,6 +66,39 @@ __device__ __forceinline__ Carry<T> carry_combine(const SR &sr, const Carry<T> &
     return r;
 }
 
+
+// ------------------------------------------------------------------ write-back fused into the row emission
+// w<M, replace> accum= t, applied in registers at the moment a row's reduction is complete.
+// `active == 0` means plain T output (no mask, no accumulator).  c_* is the OLD content of the output vector.
+template <typename T> struct VecEpi {
+    const T *c_vals; const uint8_t *c_present; const uint8_t *mask;
+    int active, has_mask, comp, replace, accum;
+};
+template <typename T>
+__device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, int tp, T *__restrict__ w_vals,
+                                          uint8_t *__restrict__ w_present) {
+    if (!e.active) {
+        w_vals[row] = tp ? t : T();
+        w_present[row] = (uint8_t)tp;
+        return;
+    }
+    const bool m = e.has_mask ? ((e.mask[row] != 0) != (e.comp != 0)) : !e.comp;
+    const bool cp = e.c_present ? e.c_present[row] != 0 : false;
+    const T c = cp ? e.c_vals[row] : T();
+    T z = t;
+    bool zp = tp != 0;
+    if (e.accum != OP_NONE && cp) {
+        z = zp ? binop<T>(e.accum, c, z) : c;
+        zp = true;
+    }
+    if (!m) {
+        if (e.replace) zp = false;
+        else { z = c; zp = cp; }
+    }
+    w_vals[row] = zp ? z : T();
+    w_present[row] = zp ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ merge-path tile search
 __global__ void merge_search_kernel(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t nnz, int tile_items,
                                     int64_t n_tiles, int64_t *__restrict__ tile_starts) {
@@ -85,12 +118,12 @@ __global__ void merge_search_kernel(const int64_t *__restrict__ rowptr, int64_t 
 
 // ------------------------------------------------------------------ merge-path SpMV
 template <typename SR, typename T, bool XFULL>
-__global__ void __launch_bounds__(SPMV_BLOCK)
+__global__ void __launch_bounds__(SPMV_BLOCK, (sizeof(T) >= 8 ? 6 : 8))
 spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__ rowptr,
                   const int32_t *__restrict__ colidx, const T *__restrict__ avals, const T *__restrict__ x,
                   const uint8_t *__restrict__ xp, const int64_t *__restrict__ tile_starts, bool flip,
                   T *__restrict__ t_vals, uint8_t *__restrict__ t_present, int64_t *__restrict__ carry_row,
-                  T *__restrict__ carry_val, uint8_t *__restrict__ carry_has) {
+                  T *__restrict__ carry_val, uint8_t *__restrict__ carry_has, VecEpi<T> epi) {
     constexpr int IPT = SpmvCfg<T>::IPT;
     constexpr int TILE = SPMV_BLOCK * IPT;
     __shared__ int s_rowend[TILE + 1];
@@ -108,6 +141,7 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
     const int tile_rows = (int)(r1 - r0), tile_nnz = (int)(k1 - k0);
     const int tile_items = tile_rows + tile_nnz;
 
+    const bool carry_in = rowptr[r0 < nrows ? r0 : nrows] < k0;   // the tile's first row began in an earlier tile
     for (int i = tid; i < tile_rows; i += SPMV_BLOCK) s_rowend[i] = (int)(rowptr[r0 + i + 1] - k0);
     if (tid == 0) s_rowend[tile_rows] = INT_MAX;
 
@@ -230,8 +264,12 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
                 h = 1;
             }
             const int64_t row = r0 + x_first + e;
-            t_vals[row] = h ? v : sr.identity();
-            t_present[row] = (uint8_t)h;
+            if (e == 0 && x_first == 0 && carry_in) {   // earlier tiles hold part of this row: the fix-up kernel finishes it
+                t_vals[row] = h ? v : T();
+                t_present[row] = (uint8_t)h;
+            } else {
+                epi_write(epi, row, v, h, t_vals, t_present);
+            }
         }
     }
     // tile carry-out: partial sum of the row that continues into the next tile
@@ -244,17 +282,23 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
     }
 }
 
-// cross-tile fix-up: the last tile that carries into a row folds the whole chain of carries into it
+// cross-tile fix-up: the last tile that carries into a row folds the whole chain of carries into the partial left by
+// the tile where the row ends, then applies the write-back (that tile deferred it -- same predicate on both sides:
+// the row began before the first nonzero of the tile in which it ends).
 template <typename SR, typename T>
-__global__ void spmv_merge_fixup_kernel(SR sr, int64_t n_tiles, int64_t nrows, const int64_t *__restrict__ carry_row,
+__global__ void spmv_merge_fixup_kernel(SR sr, int64_t n_tiles, int64_t nrows, int tile_items, const int64_t *__restrict__ rowptr,
+                                        const int64_t *__restrict__ tile_starts, const int64_t *__restrict__ carry_row,
                                         const T *__restrict__ carry_val, const uint8_t *__restrict__ carry_has,
-                                        T *__restrict__ t_vals, uint8_t *__restrict__ t_present) {
+                                        T *__restrict__ t_vals, uint8_t *__restrict__ t_present, VecEpi<T> epi) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    int64_t row = carry_row[t];
+    const int64_t row = carry_row[t];
     if (row >= nrows) return;
-    if (t + 1 < n_tiles && carry_row[t + 1] == row) return;  // a later tile owns this chain
-    T acc = sr.identity();
+    if (t + 1 >= n_tiles) return;                      // cannot happen for row < nrows (the last tile consumes every row end)
+    if (carry_row[t + 1] == row) return;               // a later tile owns this chain
+    const int64_t k0_next = (t + 1) * (int64_t)tile_items - tile_starts[t + 1];
+    if (rowptr[row] >= k0_next) return;                // the row starts in the next tile: it was emitted there, complete
+    T acc = T();
     int has = 0;
     for (int64_t q = t; q >= 0 && carry_row[q] == row; q--) {
         if (carry_has[q]) {
@@ -262,9 +306,11 @@ __global__ void spmv_merge_fixup_kernel(SR sr, int64_t n_tiles, int64_t nrows, c
             has = 1;
         }
     }
-    if (!has) return;
-    if (t_present[row]) t_vals[row] = sr.add(acc, t_vals[row]);
-    else { t_vals[row] = acc; t_present[row] = 1; }
+    if (t_present[row]) {
+        acc = has ? sr.add(acc, t_vals[row]) : t_vals[row];
+        has = 1;
+    }
+    epi_write(epi, row, acc, has, t_vals, t_present);
 }
 
 // ------------------------------------------------------------------ warp-per-row pull with mask skip / ANY early exit
@@ -273,15 +319,15 @@ __global__ void __launch_bounds__(256)
 spmv_rowwarp_kernel(SR sr, int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                     const T *__restrict__ avals, const T *__restrict__ x, const uint8_t *__restrict__ xp, bool flip,
                     const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
-                    uint8_t *__restrict__ t_present) {
+                    uint8_t *__restrict__ t_present, VecEpi<T> epi) {
     const int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = w; i < nrows; i += nw) {
         if (mask) {
             bool m = (mask[i] != 0) != mask_comp;
-            if (!m) {  // the write-back will discard T(i) anyway
-                if (lane == 0) { t_present[i] = 0; t_vals[i] = sr.identity(); }
+            if (!m) {  // masked out: T(i) is irrelevant, the row is never read
+                if (lane == 0) epi_write(epi, i, T(), 0, t_vals, t_present);
                 continue;
             }
         }
@@ -309,10 +355,7 @@ spmv_rowwarp_kernel(SR sr, int64_t nrows, const int64_t *__restrict__ rowptr, co
                 has = 1;
             }
         }
-        if (lane == 0) {
-            t_vals[i] = has ? acc : sr.identity();
-            t_present[i] = (uint8_t)has;
-        }
+        if (lane == 0) epi_write(epi, i, acc, has, t_vals, t_present);
     }
 }
 
@@ -389,7 +432,7 @@ static GrB_Info ensure_tiles(CsrArrays &c, int64_t nrows, int64_t nnz, int tile_
 template <typename SR, typename T>
 static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz, const T *avals, const T *x, int64_t x_len,
                          const uint8_t *xp, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
-                         uint8_t *t_present, std::string *err) {
+                         uint8_t *t_present, const VecEpi<T> &epi, std::string *err) {
     if (mrows == 0) return GrB_SUCCESS;
     const char *method = opt_get("spmv", "auto");
     bool use_rowwarp = !strcmp(method, "rowwarp") || (!strcmp(method, "auto") && mask != nullptr);
@@ -397,8 +440,8 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
         int64_t warps_needed = mrows;
         int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)g_num_sms * 32);
         LAUNCH_NOTE("spmv_rowwarp");
-        if (xp) spmv_rowwarp_kernel<SR, T, false><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present);
-        else spmv_rowwarp_kernel<SR, T, true><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present);
+        if (xp) spmv_rowwarp_kernel<SR, T, false><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present, epi);
+        else spmv_rowwarp_kernel<SR, T, true><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present, epi);
         CUDA_TRY(err, cudaGetLastError());
         return GrB_SUCCESS;
     }
@@ -414,12 +457,12 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
     }
     {
         LAUNCH_NOTE("spmv_merge");
-        if (xp) spmv_merge_kernel<SR, T, false><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has);
-        else spmv_merge_kernel<SR, T, true><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has);
+        if (xp) spmv_merge_kernel<SR, T, false><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has, epi);
+        else spmv_merge_kernel<SR, T, true><<<(unsigned)n_tiles, SPMV_BLOCK, 0, g_stream>>>(sr, mrows, nnz, M.ptr, M.idx, avals, x, xp, M.tile_starts, flip, t_vals, t_present, carry_row, carry_val, carry_has, epi);
     }
     {
         LAUNCH_NOTE("spmv_merge_fixup");
-        spmv_merge_fixup_kernel<SR, T><<<(unsigned)((n_tiles + 255) / 256), 256, 0, g_stream>>>(sr, n_tiles, mrows, carry_row, carry_val, carry_has, t_vals, t_present);
+        spmv_merge_fixup_kernel<SR, T><<<(unsigned)((n_tiles + 255) / 256), 256, 0, g_stream>>>(sr, n_tiles, mrows, TILE, M.ptr, M.tile_starts, carry_row, carry_val, carry_has, t_vals, t_present, epi);
     }
     cudaError_t e = cudaGetLastError();
     dev_free(carry_row); dev_free(carry_val); dev_free(carry_has);
@@ -462,6 +505,7 @@ static GrB_Info run_push(const SR &sr, const CsrArrays &A, int64_t arows, int64_
 struct MatVecArgs {
     GrB_Matrix A; bool use_transpose; GrB_Vector u; bool flip; const uint8_t *mask; bool mask_comp;
     int add, mul; int64_t out_len; void *t_vals; uint8_t *t_present; std::string *err;
+    const VecEpiHost *epi; bool *fused;
 };
 
 template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
@@ -508,9 +552,18 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             if (push)
                 info = run_push<SRT, T>(sr, A->csr, A->nrows, a.out_len, (const T *)av, (const T *)uv, u->present,
                                         u->nvals, kflip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
-            else
+            else {
+                VecEpi<T> epi;
+                memset(&epi, 0, sizeof epi);
+                if (a.epi) {   // pull kernels finish every row exactly once: the write-back is applied there, in registers
+                    epi.active = 1;
+                    epi.c_vals = (const T *)a.epi->c_vals; epi.c_present = a.epi->c_present; epi.mask = a.epi->mask;
+                    epi.has_mask = a.epi->has_mask; epi.comp = a.epi->comp; epi.replace = a.epi->replace; epi.accum = a.epi->accum;
+                    if (a.fused) *a.fused = true;
+                }
                 info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, u->n, up, kflip, a.mask,
-                                        a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
+                                        a.mask_comp, (T *)a.t_vals, a.t_present, epi, a.err);
+            }
         }
         dev_free(atmp);
         dev_free(utmp);
@@ -521,7 +574,8 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
 // mask_eff: byte array (1 = mask entry counts) or nullptr; see api.cu for how value masks are reduced to bytes
 GrB_Info multiply_mat_vec_impl(void **t_vals_out, uint8_t **t_present_out, int64_t *t_len, const GrB_Semiring op,
                                GrB_Matrix A, bool use_transpose, GrB_Vector u, bool flip, const uint8_t *mask_eff,
-                               bool mask_comp, std::string *err) {
+                               bool mask_comp, std::string *err, const VecEpiHost *epi, bool *fused) {
+    if (fused) *fused = false;
     const int64_t out_len = use_transpose ? A->ncols : A->nrows;
     const int64_t in_len = use_transpose ? A->nrows : A->ncols;
     if (u->n != in_len)
@@ -534,7 +588,7 @@ GrB_Info multiply_mat_vec_impl(void **t_vals_out, uint8_t **t_present_out, int64
     void *tv = dev_alloc(n * type_size(D));
     uint8_t *tp = (uint8_t *)dev_alloc(n);
     if (!tv || !tp) { dev_free(tv); dev_free(tp); return set_error(err, GrB_OUT_OF_MEMORY, "result vector"); }
-    MatVecArgs a{A, use_transpose, u, flip, mask_eff, mask_comp, op->add, op->mul, out_len, tv, tp, err};
+    MatVecArgs a{A, use_transpose, u, flip, mask_eff, mask_comp, op->add, op->mul, out_len, tv, tp, err, epi, fused};
     GrB_Info info = GrB_NOT_IMPLEMENTED;
     GRB_DISPATCH_TYPE(D, T, info = mat_vec_typed<T>(a));
     if (info) { dev_free(tv); dev_free(tp); return info; }

@@ -153,3 +153,34 @@ def test_bfs_and_sssp_optimality_conditions(gb, torch):
     assert bool((Df[cols] <= Df[rows] + w)[DP[rows]].all())                 # no edge can be relaxed further
     bestd = torch.full((n,), INF, dtype=torch.int64, device=dev).scatter_reduce(0, cols, Df[rows] + w, "amin")
     assert torch.equal(bestd[reached], D[reached]) and int(D[src]) == 0      # every distance is realised by an in-edge
+
+
+def test_masked_mxm_graph500_scale22(gb, torch):
+    """BASELINE config 2b: C<A.S> = A (+).(x) A on the Graph500-skew matrix (1.46e11 multiply-adds; the unmasked product
+    would be ~0.5 TB).  Checks: result pattern is a subset of the mask, and on a slice of rows the in-hash masked path
+    agrees exactly with forming the unmasked product and masking afterwards."""
+    import bench
+
+    ip, c, n = _rmat(torch, bench.RMAT_2B)
+    dev = c.device
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    v = torch.randint(1, 4, (c.numel(),), device=dev, generator=g, dtype=torch.int32)
+    A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
+    C = A.mxm(A, gb.semiring.plus_times).new(mask=A.S)
+    assert 0 < C.nvals <= A.nvals
+    # slice: 20000 low-degree rows of A against the full A, both paths
+    r0, r1 = n // 2, n // 2 + 20000
+    k0, k1 = int(ip[r0]), int(ip[r1])
+    As = gb.cuda.matrix_from_device_csr((ip[r0:r1 + 1] - k0).contiguous(), c[k0:k1].contiguous(), v[k0:k1].contiguous(), r1 - r0, n)
+    fast = As.mxm(A, gb.semiring.plus_times).new(mask=As.S)
+    gb.cuda.set_option("spgemm_mask", "0")
+    try:
+        slow = As.mxm(A, gb.semiring.plus_times).new(mask=As.S)
+    finally:
+        gb.cuda.set_option("spgemm_mask", "1")
+    assert fast.isequal(slow)
+    # the full result restricted to those rows equals the slice result
+    Cp, Cj, Cx = C.to_csr()
+    Fp, Fj, Fx = fast.to_csr()
+    a, b = int(Cp[r0]), int(Cp[r1])
+    assert np.array_equal(Cp[r0:r1 + 1] - Cp[r0], Fp) and np.array_equal(Cj[a:b], Fj) and np.array_equal(Cx[a:b], Fx)

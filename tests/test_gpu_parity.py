@@ -355,6 +355,23 @@ def test_rmat_parity(gb, scale):
     want = R.mxv_T("plus_times", R.BigMat.from_coo(r, c, wf, n, n), R.BigVec(xf, np.ones(n, np.uint8)))
     ok, msg = H.vec_equal(got, want, rtol=1e-4)
     assert ok, msg
+    # masked product: in-hash mask (tables pre-loaded with the mask rows) vs the oracle, and vs the post-hoc masked path
+    Ms = A.mxm(A, gb.semiring.plus_times).new(mask=A.S)
+    want = R.mxm(R.BigMat(np.zeros(n + 1), [], np.zeros(0, np.int64), n, n), Ab, None, "plus_times", Ab, Ab, structure=True)
+    ok, msg = H.mat_equal(Ms, want)
+    assert ok, "masked " + msg
+    gb.cuda.set_option("spgemm_mask", "0")
+    try:
+        Ms2 = A.mxm(A, gb.semiring.plus_times).new(mask=A.S)
+    finally:
+        gb.cuda.set_option("spgemm_mask", "1")
+    assert Ms2.isequal(Ms)
+    mv = rng.integers(0, 2, r.size).astype(np.int8)          # value mask: only truthy entries count
+    Mv = gb.Matrix.from_coo(r, c, mv, nrows=n, ncols=n)
+    got = A.mxm(A, gb.semiring.min_plus).new(mask=Mv.V)
+    want = R.mxm(R.BigMat(np.zeros(n + 1), [], np.zeros(0, np.int64), n, n), R.BigMat.from_coo(r, c, mv, n, n), None, "min_plus", Ab, Ab)
+    ok, msg = H.mat_equal(got, want)
+    assert ok, "value-masked " + msg
     if scale <= 10:
         C = A.mxm(A, gb.semiring.plus_times).new()
         ok, msg = H.mat_equal(C, R.mxm_T("plus_times", Ab, Ab))
