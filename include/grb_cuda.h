@@ -227,6 +227,9 @@ GrB_Info GrB_cuda_mxm_symbolic(GrB_Index *flops, GrB_Index *nvals_out, const GrB
 /* streams / timing / options / introspection */
 GrB_Info GrB_cuda_set_stream(void *cuda_stream); /* NULL restores the library's own stream */
 void *GrB_cuda_get_stream(void);
+/* order the library stream against another CUDA stream without a host sync: direction 0 = library waits for `other`,
+   1 = `other` waits for the library; NULL / (void*)1 = the legacy NULL stream */
+GrB_Info GrB_cuda_stream_order(void *other_stream, int direction);
 GrB_Info GrB_cuda_sync(void);
 GrB_Info GrB_cuda_set_device(int device);
 GrB_Info GrB_cuda_timer_start(void);          /* cudaEventRecord on the library stream */

@@ -45,6 +45,19 @@ struct CsrArrays {
     int64_t *tile_starts = nullptr;  // merge-path tile row coordinates (cached; see spmv.cu)
     int64_t n_tiles = 0;
     int tile_items = 0;
+    // hot-column cache for pull SpMV (spmv.cu / hotcols.cu): the most referenced columns of this CSR, by rank
+    int32_t *hot_remap = nullptr;    // nvals: column index, or HOT_FLAG | rank for a hot column
+    int32_t *hot_cols = nullptr;     // hot_n: rank -> column
+    int64_t *hot_prefix = nullptr;   // HOST array (malloc): references covered by ranks 0..r
+    int hot_n = 0;
+    int hot_state = 0;               // 0 not analysed, 1 built, -1 not worthwhile
+    int pull_calls = 0;              // pull SpMV calls seen (the analysis is paid for on the second one)
+    // row-boundary metadata of the segmented pull SpMV (spmv_seg.cu), built on first use
+    uint8_t *seg_flags = nullptr;    // bit (k & 7) of byte (k >> 3): entry k is the first of its row
+    int32_t *seg_rows = nullptr;     // rows that have at least one entry, ascending
+    int32_t *seg_tile_ord = nullptr; // per 128 entries: ordinal (in seg_rows) of the row in progress before the tile
+    int64_t seg_nonempty = 0;
+    int seg_state = 0;               // 0 not built, 1 built
 };
 
 struct GrB_Matrix_opaque {
@@ -108,6 +121,9 @@ static inline bool valid(const GrB_Vector v) { return v && v->magic == GRB_MAGIC
 
 // object helpers (objects.cu)
 void csr_free(CsrArrays &c);
+void csr_drop_hot(CsrArrays &c);                   // forget the hot-column cache (column order changed)
+void csr_drop_seg(CsrArrays &c);
+GrB_Info csr_ensure_hot(CsrArrays &c, int64_t ncols, int64_t nvals, int max_hot, std::string *err);   // hotcols.cu
 void matrix_drop_twin(GrB_Matrix A);
 void matrix_release(GrB_Matrix A);                 // free device arrays, keep shell
 GrB_Info matrix_alloc_csr(GrB_Matrix A, int64_t nvals);  // allocates csr.ptr/idx/val for nvals entries

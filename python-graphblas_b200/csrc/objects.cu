@@ -31,11 +31,36 @@ int64_t read_i64(const int64_t *dptr) {
 }
 
 // ------------------------------------------------------------------ matrix storage
+void csr_drop_hot(CsrArrays &c) {
+    dev_free(c.hot_remap);
+    dev_free(c.hot_cols);
+    free(c.hot_prefix);
+    c.hot_remap = nullptr;
+    c.hot_cols = nullptr;
+    c.hot_prefix = nullptr;
+    c.hot_n = 0;
+    c.hot_state = 0;
+    c.pull_calls = 0;
+}
+
+void csr_drop_seg(CsrArrays &c) {
+    dev_free(c.seg_flags);
+    dev_free(c.seg_rows);
+    dev_free(c.seg_tile_ord);
+    c.seg_flags = nullptr;
+    c.seg_rows = nullptr;
+    c.seg_tile_ord = nullptr;
+    c.seg_nonempty = 0;
+    c.seg_state = 0;
+}
+
 void csr_free(CsrArrays &c) {
     dev_free(c.ptr);
     dev_free(c.idx);
     dev_free(c.val);
     dev_free(c.tile_starts);
+    csr_drop_hot(c);
+    csr_drop_seg(c);
     c = CsrArrays();
 }
 

@@ -255,6 +255,22 @@ extern "C" GrB_Info GrB_cuda_set_stream(void *s) {
 }
 extern "C" void *GrB_cuda_get_stream(void) { return (void *)g_stream; }
 
+// Stream ordering without a host synchronisation.  direction 0: the library stream waits for everything enqueued so
+// far on `other` (call BEFORE handing device buffers produced on `other` to the library); direction 1: `other` waits
+// for the library stream (call AFTER, before `other` frees / reuses those buffers or reads library-owned arrays).
+// `other` == NULL or (void*)1 names the legacy NULL stream.
+extern "C" GrB_Info GrB_cuda_stream_order(void *other, int direction) {
+    CHECK_INIT();
+    cudaStream_t o = (other == nullptr || other == (void *)1) ? cudaStreamLegacy : (cudaStream_t)other;
+    if (o == g_stream) return GrB_SUCCESS;
+    static cudaEvent_t ev = nullptr;
+    if (!ev) CUDA_TRY(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaStream_t first = direction == 0 ? o : g_stream, second = direction == 0 ? g_stream : o;
+    CUDA_TRY(nullptr, cudaEventRecord(ev, first));
+    CUDA_TRY(nullptr, cudaStreamWaitEvent(second, ev, 0));
+    return GrB_SUCCESS;
+}
+
 extern "C" GrB_Info GrB_cuda_sync(void) {
     CHECK_INIT();
     CUDA_TRY(nullptr, cudaStreamSynchronize(g_stream));

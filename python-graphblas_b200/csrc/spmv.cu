@@ -15,44 +15,12 @@
 // Serves: GrB_mxv (reference core/matrix.py:2252-2259), GrB_vxm (core/vector.py:1368-1375).
 #include <limits.h>
 
-#include "grb_ops.cuh"
+#include "spmv_common.cuh"
 
 constexpr int SPMV_BLOCK = 256;
 
 // items per thread: odd, so that the per-thread walk over shared memory (stride IPT words) is bank-conflict free
 template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? 5 : 7); };
-
-// ---- shuffle helpers for arbitrary 1..8 byte value types ----
-template <typename T> __device__ __forceinline__ T shfl_up_any(T v, int delta) {
-    if constexpr (sizeof(T) == 8) {
-        unsigned long long b;
-        memcpy(&b, &v, 8);
-        b = __shfl_up_sync(0xffffffffu, b, delta);
-        memcpy(&v, &b, 8);
-        return v;
-    } else {
-        unsigned int b = 0;
-        memcpy(&b, &v, sizeof(T));
-        b = __shfl_up_sync(0xffffffffu, b, delta);
-        memcpy(&v, &b, sizeof(T));
-        return v;
-    }
-}
-template <typename T> __device__ __forceinline__ T shfl_down_any(T v, int delta) {
-    if constexpr (sizeof(T) == 8) {
-        unsigned long long b;
-        memcpy(&b, &v, 8);
-        b = __shfl_down_sync(0xffffffffu, b, delta);
-        memcpy(&v, &b, 8);
-        return v;
-    } else {
-        unsigned int b = 0;
-        memcpy(&b, &v, sizeof(T));
-        b = __shfl_down_sync(0xffffffffu, b, delta);
-        memcpy(&v, &b, sizeof(T));
-        return v;
-    }
-}
 
 // (row, value, has) triple of a partially reduced row; combine = reduce-by-key, associative
 template <typename T> struct Carry { int row; int has; T val; };
@@ -66,38 +34,6 @@ __device__ __forceinline__ Carry<T> carry_combine(const SR &sr, const Carry<T> &
     return r;
 }
 
-
-// ------------------------------------------------------------------ write-back fused into the row emission
-// w<M, replace> accum= t, applied in registers at the moment a row's reduction is complete.
-// `active == 0` means plain T output (no mask, no accumulator).  c_* is the OLD content of the output vector.
-template <typename T> struct VecEpi {
-    const T *c_vals; const uint8_t *c_present; const uint8_t *mask;
-    int active, has_mask, comp, replace, accum;
-};
-template <typename T>
-__device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, int tp, T *__restrict__ w_vals,
-                                          uint8_t *__restrict__ w_present) {
-    if (!e.active) {
-        w_vals[row] = tp ? t : T();
-        w_present[row] = (uint8_t)tp;
-        return;
-    }
-    const bool m = e.has_mask ? ((e.mask[row] != 0) != (e.comp != 0)) : !e.comp;
-    const bool cp = e.c_present ? e.c_present[row] != 0 : false;
-    const T c = cp ? e.c_vals[row] : T();
-    T z = t;
-    bool zp = tp != 0;
-    if (e.accum != OP_NONE && cp) {
-        z = zp ? binop<T>(e.accum, c, z) : c;
-        zp = true;
-    }
-    if (!m) {
-        if (e.replace) zp = false;
-        else { z = c; zp = cp; }
-    }
-    w_vals[row] = zp ? z : T();
-    w_present[row] = zp ? 1 : 0;
-}
 
 // ------------------------------------------------------------------ merge-path tile search
 __global__ void merge_search_kernel(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t nnz, int tile_items,
@@ -444,6 +380,12 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
         else spmv_rowwarp_kernel<SR, T, true><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present, epi);
         CUDA_TRY(err, cudaGetLastError());
         return GrB_SUCCESS;
+    }
+    if (!strcmp(method, "auto") || !strcmp(method, "seg")) {   // default: segmented kernel (spmv_seg.cu)
+        bool handled = false;
+        GRB_TRY(spmv_seg_run(type_code_of<T>(), sr.add_op(), sr.mul_op(), M, mrows, x_len, nnz, avals, x, xp, t_vals, t_present,
+                             &epi, err, &handled));
+        if (handled) return GrB_SUCCESS;
     }
     constexpr int TILE = SPMV_BLOCK * SpmvCfg<T>::IPT;
     GRB_TRY(ensure_tiles(M, mrows, nnz, TILE, err));

@@ -1,0 +1,90 @@
+// spmv_common.cuh -- pieces shared by the pull SpMV kernels (spmv.cu: merge-path / warp-per-row; spmv_seg.cu: segmented).
+#pragma once
+#include "grb_ops.cuh"
+
+// ---- shuffle helpers for arbitrary 1..8 byte value types ----
+template <typename T> __device__ __forceinline__ T shfl_up_any(T v, int delta) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        b = __shfl_up_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, 8);
+        return v;
+    } else {
+        unsigned int b = 0;
+        memcpy(&b, &v, sizeof(T));
+        b = __shfl_up_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, sizeof(T));
+        return v;
+    }
+}
+template <typename T> __device__ __forceinline__ T shfl_down_any(T v, int delta) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        b = __shfl_down_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, 8);
+        return v;
+    } else {
+        unsigned int b = 0;
+        memcpy(&b, &v, sizeof(T));
+        b = __shfl_down_sync(0xffffffffu, b, delta);
+        memcpy(&v, &b, sizeof(T));
+        return v;
+    }
+}
+
+template <typename T> __device__ __forceinline__ T shfl_any(T v, int src_lane) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        b = __shfl_sync(0xffffffffu, b, src_lane);
+        memcpy(&v, &b, 8);
+        return v;
+    } else {
+        unsigned int b = 0;
+        memcpy(&b, &v, sizeof(T));
+        b = __shfl_sync(0xffffffffu, b, src_lane);
+        memcpy(&v, &b, sizeof(T));
+        return v;
+    }
+}
+
+// ------------------------------------------------------------------ write-back fused into the row emission
+// w<M, replace> accum= t, applied in registers at the moment a row's reduction is complete.
+// `active == 0` means plain T output (no mask, no accumulator).  c_* is the OLD content of the output vector.
+template <typename T> struct VecEpi {
+    const T *c_vals; const uint8_t *c_present; const uint8_t *mask;
+    int active, has_mask, comp, replace, accum;
+};
+template <typename T>
+__device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, int tp, T *__restrict__ w_vals,
+                                          uint8_t *__restrict__ w_present) {
+    if (!e.active) {
+        w_vals[row] = tp ? t : T();
+        w_present[row] = (uint8_t)tp;
+        return;
+    }
+    const bool m = e.has_mask ? ((e.mask[row] != 0) != (e.comp != 0)) : !e.comp;
+    const bool cp = e.c_present ? e.c_present[row] != 0 : false;
+    const T c = cp ? e.c_vals[row] : T();
+    T z = t;
+    bool zp = tp != 0;
+    if (e.accum != OP_NONE && cp) {
+        z = zp ? binop<T>(e.accum, c, z) : c;
+        zp = true;
+    }
+    if (!m) {
+        if (e.replace) zp = false;
+        else { z = c; zp = cp; }
+    }
+    w_vals[row] = zp ? z : T();
+    w_present[row] = zp ? 1 : 0;
+}
+
+
+// segmented pull SpMV (spmv_seg.cu).  Returns GrB_SUCCESS with *handled = false when the inputs do not fit the kernel
+// (unaligned arrays); the caller then falls back to the merge-path kernel.  `epi` may be null (plain T output).
+GrB_Info spmv_seg_run(int type_code, int add_op, int mul_op, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz,
+                      const void *avals, const void *x, const uint8_t *xp, void *t_vals, uint8_t *t_present,
+                      const void *epi_typed, std::string *err, bool *handled);

@@ -246,6 +246,7 @@ GrB_Info matrix_ensure_sorted(GrB_Matrix A) {
         default: info = sort_rows_typed<uint64_t>(A); break;
     }
     if (!info) A->jumbled = false;
+    csr_drop_hot(A->csr);   // positions of the column indices moved
     return info;
 }
 

@@ -38,6 +38,24 @@ def use_torch_stream():
     call("GrB_cuda_set_stream", [ctypes.c_void_p(h if h else 1)])   # 1 == cudaStreamLegacy (the NULL stream)
 
 
+def _torch_stream_handle():
+    import torch
+
+    h = torch.cuda.current_stream().cuda_stream
+    return ctypes.c_void_p(h if h else 1)
+
+
+def _wait_for_torch():
+    """library stream waits for torch's current stream (torch-produced inputs are complete before we read them)"""
+    call("GrB_cuda_stream_order", [_torch_stream_handle(), 0])
+
+
+def _torch_waits():
+    """torch's current stream waits for the library stream (our reads of torch buffers finish before torch reuses them;
+    library-owned arrays are complete before torch reads them)"""
+    call("GrB_cuda_stream_order", [_torch_stream_handle(), 1])
+
+
 def timer_start():
     call("GrB_cuda_timer_start", [])
 
@@ -73,10 +91,12 @@ def matrix_from_device_csr(indptr, col_indices, values, nrows, ncols, *, sorted=
     assert col_indices.element_size() == 4
     h = ctypes.c_void_p()
     out = Matrix._from_handle(h, dtype, nrows, ncols, name)
+    _wait_for_torch()
     call("GrB_cuda_Matrix_import_csr32",
          [ctypes.byref(h), dtype, GrB_Index(nrows), GrB_Index(ncols), ctypes.c_void_p(indptr.data_ptr()),
           ctypes.c_void_p(col_indices.data_ptr()), ctypes.c_void_p(values.data_ptr()), GrB_Index(col_indices.numel()),
           1, 1 if sorted else 0])
+    _torch_waits()
     return out
 
 
@@ -124,9 +144,11 @@ def vector_from_torch(values, present=None, *, name=None):
     dtype = lookup_dtype(_torch_dtype(values.dtype))
     h = ctypes.c_void_p()
     out = Vector._from_handle(h, dtype, values.numel(), name)
+    _wait_for_torch()
     call("GrB_cuda_Vector_import_dense",
          [ctypes.byref(h), dtype, GrB_Index(values.numel()), ctypes.c_void_p(values.data_ptr()),
           None if present is None else ctypes.c_void_p(present.data_ptr()), 1])
+    _torch_waits()
     return out
 
 
@@ -169,6 +191,8 @@ def vector_as_torch(v, sync=True):
 
     if sync:
         globals()["sync"]()
+    else:
+        _torch_waits()
 
     pv, pp = vector_device_pointers(v)
     n = v.size

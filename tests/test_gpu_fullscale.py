@@ -48,8 +48,9 @@ def test_mxv_degree_identities(gb, torch):
     A = gb.cuda.matrix_from_device_csr(ip, c, ones, n, n)
     x = gb.cuda.vector_from_torch(torch.ones(n, dtype=torch.float32, device=c.device))
     results = {}
-    for method in ("merge", "rowwarp"):
-        gb.cuda.set_option("spmv", method)
+    for method in ("merge", "hot", "rowwarp"):
+        gb.cuda.set_option("spmv", "merge" if method == "hot" else method)
+        gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")   # hot-column cache of the pull kernel forced / off
         y = A.mxv(x, gb.semiring.plus_times).new()
         vals, pres = _vec_to_torch(gb, torch, y)
         assert torch.equal(pres.bool(), deg > 0)
@@ -60,6 +61,7 @@ def test_mxv_degree_identities(gb, torch):
         zv, zp = _vec_to_torch(gb, torch, z)
         assert torch.equal(zp.bool(), deg > 0) and bool((zv[deg > 0] == 1).all())
     gb.cuda.set_option("spmv", "auto")
+    gb.cuda.set_option("spmv_hot", "auto")
     # int64 min_plus with x = 0: y(i) = min weight of row i; compare with a torch segmented min; both kernels bit-exact
     g = torch.Generator(device=c.device); g.manual_seed(7)
     w = torch.randint(1, 256, (c.numel(),), device=c.device, generator=g, dtype=torch.int64)
@@ -67,12 +69,27 @@ def test_mxv_degree_identities(gb, torch):
     x0 = gb.cuda.vector_from_torch(torch.zeros(n, dtype=torch.int64, device=c.device))
     rows = torch.repeat_interleave(torch.arange(n, device=c.device), deg)
     want = torch.full((n,), 1 << 62, dtype=torch.int64, device=c.device).scatter_reduce(0, rows, w, "amin")
-    for method in ("merge", "rowwarp"):
-        gb.cuda.set_option("spmv", method)
+    for method in ("merge", "hot", "rowwarp"):
+        gb.cuda.set_option("spmv", "merge" if method == "hot" else method)
+        gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")
         y = W.mxv(x0, gb.semiring.min_plus).new()
         vals, pres = _vec_to_torch(gb, torch, y)
         assert torch.equal(vals[deg > 0], want[deg > 0]), method
     gb.cuda.set_option("spmv", "auto")
+    gb.cuda.set_option("spmv_hot", "auto")
+    # random x (fp64, exactly summable small integers): hot-cache kernel == plain merge kernel bit-exactly, incl. sparse x
+    g2 = torch.Generator(device=c.device); g2.manual_seed(9)
+    xr = torch.randint(0, 8, (n,), device=c.device, generator=g2).to(torch.float64)
+    pr = (torch.rand(n, device=c.device, generator=g2) < 0.7).to(torch.uint8)
+    Ad = gb.cuda.matrix_from_device_csr(ip, c, torch.ones(c.numel(), dtype=torch.float64, device=c.device), n, n)
+    for present in (None, pr):
+        xv = gb.cuda.vector_from_torch(xr, present)
+        outs = []
+        for hot in ("0", "1"):
+            gb.cuda.set_option("spmv_hot", hot)
+            outs.append(_vec_to_torch(gb, torch, Ad.mxv(xv, gb.semiring.plus_times).new()))
+        gb.cuda.set_option("spmv_hot", "auto")
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
     # pull over the cached transpose == push: vxm(x, A) column sums == in-degree
     indeg = torch.bincount(c.long(), minlength=n)
     for vm in ("pull", "push"):

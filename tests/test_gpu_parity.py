@@ -207,9 +207,13 @@ def test_vector_multiplies_vs_oracle(gb, semiring, dtype):
             for (use_mask, comp, struct, repl, accum) in [(False, False, False, False, None), (True, False, True, False, None),
                                                           (True, True, True, True, None), (True, False, False, True, accum_name),
                                                           (True, True, False, False, accum_name), (False, False, False, False, accum_name)]:
-                for method, vxm_method in [("merge", "pull"), ("rowwarp", "push"), ("auto", "auto")]:
+                for method, vxm_method, hot in [("merge", "pull", "0"), ("merge", "pull", "1"), ("merge", "pull", "cap"),
+                                                ("rowwarp", "push", "auto"), ("auto", "auto", "auto")]:
                     gb.cuda.set_option("spmv", method)
                     gb.cuda.set_option("vxm_method", vxm_method)
+                    # hot-column cache of the pull kernel: off / forced / forced with a 40-entry cache (ranks beyond it gather from global)
+                    gb.cuda.set_option("spmv_hot", "1" if hot == "cap" else hot)
+                    gb.cuda.set_option("spmv_hot_cap", "40" if hot == "cap" else "0")
                     u = H.gb_vector(gb, ui, uv, in_len)
                     w = H.gb_vector(gb, wi, wv, out_len)
                     kwargs = {}
@@ -237,9 +241,11 @@ def test_vector_multiplies_vs_oracle(gb, semiring, dtype):
                     else:
                         want = R.vxm(wb, mb, accum, semiring, ub, Ab, t1=True, **okw)
                     ok, msg = H.vec_equal(w, want)
-                    assert ok, (semiring, dtype, kind, trial, use_mask, comp, struct, repl, accum, method, vxm_method, msg)
+                    assert ok, (semiring, dtype, kind, trial, use_mask, comp, struct, repl, accum, method, vxm_method, hot, msg)
     gb.cuda.set_option("spmv", "auto")
     gb.cuda.set_option("vxm_method", "auto")
+    gb.cuda.set_option("spmv_hot", "auto")
+    gb.cuda.set_option("spmv_hot_cap", "0")
 
 
 @pytest.mark.parametrize("semiring", ["plus_times", "min_plus", "any_pair", "plus_second", "lor_land", "max_plus", "plus_pair"])
@@ -337,8 +343,10 @@ def test_rmat_parity(gb, scale):
     x = rng.integers(0, 1000, n).astype(np.int64)
     v = gb.Vector.from_coo(np.arange(n), x, size=n)
     vb = R.BigVec(x, np.ones(n, np.uint8))
-    for method in ("merge", "rowwarp"):
-        gb.cuda.set_option("spmv", method)
+    for method in ("merge", "hot", "hotcap", "rowwarp"):
+        gb.cuda.set_option("spmv", "merge" if method.startswith("hot") else method)
+        gb.cuda.set_option("spmv_hot", "1" if method.startswith("hot") else "0")
+        gb.cuda.set_option("spmv_hot_cap", "300" if method == "hotcap" else "0")
         for sr in ("min_plus", "plus_times", "plus_second", "any_pair"):
             ok, msg = H.vec_equal(A.mxv(v, getattr(gb.semiring, sr)).new(), R.mxv_T(sr, Ab, vb))
             assert ok, (method, sr, msg)
@@ -347,6 +355,8 @@ def test_rmat_parity(gb, scale):
             assert ok, (method, "vxm", sr, msg)
             gb.cuda.set_option("vxm_method", "auto")
     gb.cuda.set_option("spmv", "auto")
+    gb.cuda.set_option("spmv_hot", "auto")
+    gb.cuda.set_option("spmv_hot_cap", "0")
     # fp32 with a stated tolerance: summation order differs (rtol 1e-5 * sqrt(max row products) is the contract; use 1e-4)
     wf = rng.random(r.size).astype(np.float32)
     Af = gb.Matrix.from_coo(r, c, wf, nrows=n, ncols=n)
