@@ -460,6 +460,7 @@ def run_ours(args):
     if not args.no_mxv:
         del B, A
         B = A = None
+        gb.cuda.set_option("trim", "1")   # hand the cached 10-20 GB mxm blocks back before torch builds the next input
         if rank == 0:
             ip2, c2, n2 = rmat_csr_torch(scale, RMAT_2B, 42, device=dev)
             v2 = values_torch(c2.numel(), 45, torch.float32, device=dev)

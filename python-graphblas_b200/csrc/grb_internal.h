@@ -52,6 +52,8 @@ struct CsrArrays {
     int hot_n = 0;
     int hot_state = 0;               // 0 not analysed, 1 built, -1 not worthwhile
     int pull_calls = 0;              // pull SpMV calls seen (the analysis is paid for on the second one)
+    int hot_choice = 0;              // auto mode: 0 undecided, 1 plain kernel won the timed trial, 2 hot-column kernel won
+    float hot_trial_ms = -1.f;       // auto mode: time of the plain kernel in the trial (< 0: not yet run)
     // row-boundary metadata of the segmented pull SpMV (spmv_seg.cu), built on first use
     uint8_t *seg_flags = nullptr;    // bit (k & 7) of byte (k >> 3): entry k is the first of its row
     int32_t *seg_rows = nullptr;     // rows that have at least one entry, ascending
@@ -88,6 +90,7 @@ extern int g_num_sms;
 void note_launch(const char *name);
 struct KernelTimer { KernelTimer(const char *name); ~KernelTimer(); const char *name; cudaEvent_t a, b; bool on; };
 #define LAUNCH_NOTE(name) note_launch(name); KernelTimer _kt(name)
+void phase_mark(const char *name);   // option trace_host=1: host wall time since the previous mark goes to kernel-time slot "host:<name>" (nullptr: restart)
 
 GrB_Info set_error(std::string *slot, GrB_Info info, const char *fmt, ...);
 void set_last_error(const char *msg);

@@ -41,6 +41,8 @@ void csr_drop_hot(CsrArrays &c) {
     c.hot_n = 0;
     c.hot_state = 0;
     c.pull_calls = 0;
+    c.hot_choice = 0;
+    c.hot_trial_ms = -1.f;
 }
 
 void csr_drop_seg(CsrArrays &c) {

@@ -1,4 +1,5 @@
 // runtime.cu -- context, stream, stream-ordered memory, errors, options, launch accounting
+#include <chrono>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -71,6 +72,18 @@ KernelTimer::~KernelTimer() {
     }
 }
 
+void phase_mark(const char *name) {
+    static std::chrono::steady_clock::time_point last;
+    if (opt_get_int("trace_host", 0) == 0) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (name) {
+        KStat &s = g_kstats[std::string("host:") + name];
+        s.ms += std::chrono::duration<double, std::milli>(now - last).count();
+        s.n++;
+    }
+    last = std::chrono::steady_clock::now();
+}
+
 extern "C" uint64_t GrB_cuda_launch_count(void) { return g_launches; }
 
 extern "C" GrB_Info GrB_cuda_kernel_time(const char *name, double *total_ms, uint64_t *launches) {
@@ -103,13 +116,47 @@ extern "C" size_t GrB_cuda_kernel_names(char *buf, size_t buflen) {
     return need;
 }
 
+// Large blocks (>= 1 MiB) released by the library are parked in a size-keyed cache and handed out again to the next request
+// of (nearly) the same size, so an iterative workload -- the same mxm / mxv sizes every step -- does no allocator work at all
+// in steady state, not even cudaMallocAsync's pool bookkeeping (which showed up as multi-millisecond, erratic gaps between
+// steps when 10-20 GB result arrays were freed and re-allocated).  Everything the library enqueues runs on ONE stream, so
+// reuse is stream-ordered by construction; GrB_cuda_set_stream synchronises before switching.  The cache gives its blocks
+// back on allocation failure, on option "trim" and in GrB_finalize, and is bounded by option "cache_fraction" (default 0.6 of
+// device memory).
+static std::multimap<size_t, void *> g_block_cache;
+static size_t g_cache_bytes = 0, g_cache_limit = 0;
+constexpr size_t CACHE_MIN_BYTES = (size_t)1 << 20;
+
+static void cache_flush() {
+    std::multimap<size_t, void *> old;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        old.swap(g_block_cache);
+        g_cache_bytes = 0;
+    }
+    for (auto &kv : old) cudaFreeAsync(kv.second, g_stream);
+}
+
 void *dev_alloc(size_t bytes) {
     if (bytes == 0) bytes = 16;
     void *p = nullptr;
+    if (bytes >= CACHE_MIN_BYTES) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_block_cache.lower_bound(bytes);
+        if (it != g_block_cache.end() && it->first <= bytes + bytes / 8) {
+            p = it->second;
+            g_cache_bytes -= it->first;
+            g_alloc_sizes[p] = it->first;
+            g_bytes_in_use += it->first;
+            g_block_cache.erase(it);
+            return p;
+        }
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, g_stream);
     if (e != cudaSuccess) {
         // give cached blocks back and retry once
         cudaGetLastError();
+        cache_flush();
         cudaStreamSynchronize(g_stream);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -132,12 +179,27 @@ void *dev_alloc(size_t bytes) {
 
 void dev_free(void *p) {
     if (!p) return;
+    size_t bytes = 0;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_alloc_sizes.find(p);
         if (it != g_alloc_sizes.end()) {
-            g_bytes_in_use -= it->second;
+            bytes = it->second;
+            g_bytes_in_use -= bytes;
             g_alloc_sizes.erase(it);
+        }
+        if (bytes >= CACHE_MIN_BYTES && g_initialized) {
+            if (g_cache_limit == 0) {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const long pct = opt_get_int("cache_percent", 60);
+                g_cache_limit = (size_t)((double)total_b * (double)(pct < 0 ? 0 : pct) / 100.0) + 1;
+            }
+            if (g_cache_bytes + bytes <= g_cache_limit) {
+                g_block_cache.emplace(bytes, p);
+                g_cache_bytes += bytes;
+                return;
+            }
         }
     }
     cudaFreeAsync(p, g_stream);
@@ -166,6 +228,7 @@ void ws_release(int slot, void *p) {
 void ws_trim() {
     for (auto &w : g_ws)
         if (w.ptr && !w.busy) { dev_free(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+    cache_flush();
 }
 
 const char *opt_get(const char *key, const char *dflt) {

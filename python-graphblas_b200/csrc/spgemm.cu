@@ -59,8 +59,10 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
     T *vals;
     unsigned long long *ent;
     unsigned size;
-    __device__ __forceinline__ void bind(void *base, unsigned sz, void *vals_base) {
+    int cas_first;   // packed insert: claim with atomicCAS straight away instead of probing with a plain load first
+    __device__ __forceinline__ void bind(void *base, unsigned sz, void *vals_base, int casf = 0) {
         size = sz;
+        cas_first = casf;
         keys = reinterpret_cast<int *>(base);
         ent = reinterpret_cast<unsigned long long *>(base);
         vals = reinterpret_cast<T *>(vals_base);
@@ -80,6 +82,17 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
         unsigned h = hash_slot(j, size);
         if (kPacked) {
             const unsigned long long mine = pack_entry<T>(j, p);
+            if (cas_first) {   // most products of a low-compression row open a new slot: one atomic, no probe load
+                while (true) {
+                    const unsigned long long cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
+                    if (cur == HASH_EMPTY64) return 1;
+                    if ((int)(cur >> 32) == j) {
+                        atomic_combine(sr, reinterpret_cast<T *>(&ent[h]), p);
+                        return 0;
+                    }
+                    h = (h + 1 == size) ? 0 : h + 1;
+                }
+            }
             while (true) {
                 unsigned long long cur = ent[h];
                 if (cur == HASH_EMPTY64) {
@@ -190,24 +203,43 @@ __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, 
 }
 
 // ------------------------------------------------------------------ binning
-constexpr int NBINS = 11;   // 0: empty rows, 1-2: warp per row, 3-9: CTA per row (shared table), 10: global table
-struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int tf8; };
+constexpr int NBINS = 13;   // 0: empty rows, 1-2: warp per row, 3-11: CTA per row (shared table), 12: global table
+constexpr int BIN_LAST_SHARED = NBINS - 2;
+struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int tf8[NBINS]; int flags; };
+
+// shared memory of one CTA-per-row block beyond its hash table: per-thread staging of the A-row chunk
+static inline size_t block_stage_bytes(int threads, size_t val_bytes) {
+    return (size_t)threads * 8 + (size_t)((threads + 4) & ~3) * 4 + (((size_t)threads * val_bytes + 15) & ~(size_t)15);
+}
 
 static BinSpec make_bin_spec(size_t entry_bytes) {
     BinSpec s;
-    const int caps[NBINS] = {0, 64, 256, 512, 1024, 2048, 4096, 8192, 16384, 0, 0};
-    const int thr[NBINS] = {0, 256, 256, 128, 128, 256, 256, 512, 1024, 1024, 1024};   // big tables: more warps per CTA, occupancy is smem-bound
-    int maxcap = (int)((204 * 1024) / entry_bytes);   // 227 KB minus the kernel's static arrays (chunk staging for 1024 threads)
+    const int caps[NBINS] = {0, 64, 256, 512, 1024, 2048, 4096, 6144, 8192, 12288, 16384, 0, 0};
+    // small rows: narrow CTAs (a row has only a few products per thread; many independent CTAs per SM hide the dependent
+    // load chain A -> Bp -> Bj of each row); big tables: occupancy is shared-memory bound, so more warps per CTA
+    const int thr[NBINS] = {0, 256, 256, 64, 64, 128, 128, 256, 256, 512, 512, 1024, 1024};
+    int maxcap = (int)((204 * 1024) / entry_bytes);   // 227 KB minus the chunk staging of 1024 threads and the static arrays
     maxcap -= maxcap % 256;
-    for (int b = 0; b < NBINS; b++) { s.cap[b] = caps[b]; s.threads[b] = thr[b]; }
-    s.cap[9] = maxcap > 16384 + 2048 ? maxcap : 16384;
-    s.cap[10] = 0;
+    const int tf_small = std::max(10, (int)opt_get_int("spgemm_table_factor8", 20));     // table = tf8/8 x count
+    const int tf_big = std::max(10, (int)opt_get_int("spgemm_table_factor8_big", tf_small));
+    const int big_from = (int)opt_get_int("spgemm_big_from_bin", 8);
+    for (int b = 0; b < NBINS; b++) {
+        s.cap[b] = caps[b];
+        s.threads[b] = thr[b];
+        s.tf8[b] = b >= big_from ? tf_big : tf_small;
+        char key[32];
+        snprintf(key, sizeof key, "spgemm_thr_%d", b);
+        const long t = opt_get_int(key, 0);
+        if (b >= 3 && t >= 64 && t <= 1024 && t % 32 == 0) s.threads[b] = (int)t;
+    }
+    s.cap[BIN_LAST_SHARED] = maxcap > 16384 + 2048 ? maxcap : 16384;
     s.maxcount[0] = 0;
-    s.tf8 = (int)opt_get_int("spgemm_table_factor8", 20);   // table = tf8/8 x count
-    if (s.tf8 < 10) s.tf8 = 10;
-    for (int b = 1; b <= 9; b++) s.maxcount[b] = (((int64_t)s.cap[b] - 8) * 8) / s.tf8 - 1;   // tf8/8*count + 8 <= cap
-    if (s.cap[9] == 16384) s.maxcount[9] = s.maxcount[8];                            // bin 9 unused
-    s.maxcount[10] = INT64_MAX;
+    for (int b = 1; b <= BIN_LAST_SHARED; b++) {
+        s.maxcount[b] = (((int64_t)s.cap[b] - 8) * 8) / s.tf8[b] - 1;   // tf8/8*count + 8 <= cap
+        if (s.maxcount[b] < s.maxcount[b - 1]) s.maxcount[b] = s.maxcount[b - 1];   // a tighter factor must not reorder the bins
+    }
+    s.maxcount[NBINS - 1] = INT64_MAX;
+    s.flags = (opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0) | (opt_get_int("spgemm_elect", 0) != 0 ? 2 : 0);
     return s;
 }
 __device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
@@ -321,19 +353,22 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
 // template parameter so that the shared-memory instantiation compiles to ATOMS/LDS/STS rather than generic atomics.
 constexpr int UNROLL = 4;
 template <typename SR, typename T, bool NUMERIC, bool PACK, bool GLOBAL>
-__global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+__global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, int flags, const int64_t *__restrict__ cnt,
                                     const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
                                     const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
                                     int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
                                     T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets, MaskArgs mk) {
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
+    // dynamic shared memory: [hash table: cap entries (none when GLOBAL)] [s_bs: B-row starts] [s_off: product prefix] [s_av: A values]
+    // -- the staging arrays are sized by blockDim, so a 128-thread CTA of a small bin costs 2 KB, not the 16 KB of 1024 threads
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int64_t s_bs[MAX_THREADS];
-    __shared__ int s_off[MAX_THREADS + 1];
-    __shared__ T s_av[MAX_THREADS];
     __shared__ int s_wsum[MAX_THREADS / 32];
     __shared__ int s_count;
     const int tid = threadIdx.x, nthreads = blockDim.x;
+    const size_t tbytes = GLOBAL ? 0 : (((size_t)cap * Table::entry_bytes() + 15) & ~(size_t)15);
+    int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + tbytes);
+    int *s_off = reinterpret_cast<int *>(s_bs + nthreads);
+    T *s_av = reinterpret_cast<T *>(s_off + ((nthreads + 4) & ~3));
     const int64_t row = rows[blockIdx.x];
 
     Table tab;
@@ -343,9 +378,9 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         const int64_t total = g_offsets[gridDim.x];
         unsigned char *kbase = g_table + (size_t)off * (Table::kPacked ? 8 : 4);
         unsigned char *vbase = g_table + (size_t)total * 4 + (size_t)off * sizeof(T);
-        tab.bind(kbase, sz, vbase);
+        tab.bind(kbase, sz, vbase, flags & 1);
     } else {
-        tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4);
+        tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4, flags & 1);
     }
     tab.init(sr, tid, nthreads);
     if (tid == 0) s_count = 0;
@@ -355,7 +390,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
             if (!mk.Meff || mk.Meff[k]) tab.insert_mask(sr, mk.Mj[k]);
     }
 
-    const int wlane = tid & 31, warp = tid >> 5;
+    const int wlane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
     int local_new = 0;
     for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
@@ -383,25 +418,34 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         if (tid == nthreads - 1) s_off[nthreads] = base + incl;
         __syncthreads();
         const int P = s_off[nthreads];
-        for (int p0 = tid; p0 < P; p0 += nthreads * UNROLL) {
+        // A warp takes 32*UNROLL consecutive products per step: lane l handles products seg + l, seg + l + 32, ... -- consecutive
+        // lanes read consecutive entries of one B row (coalesced), and the owning A entry is found by ONE binary search per
+        // step; the later products of the lane lie 32 further on, a short forward walk over the prefix (s_off[nthreads] = P is
+        // the sentinel, entries beyond chunk_n hold P as well).
+        for (int seg = warp * (32 * UNROLL); seg < P; seg += nwarps * (32 * UNROLL)) {
             int jj[UNROLL];
             T bb[UNROLL], aa[UNROLL];
+            int p = seg + wlane;
+            int lo = 0;
+            if (p < P) {
+                int hi = chunk_n - 1;   // last entry e with s_off[e] <= p (zero-length rows are skipped)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= p) lo = mid;
+                    else hi = mid - 1;
+                }
+            }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                const int p = p0 + u * nthreads;
                 jj[u] = HASH_EMPTY;
                 if (p < P) {
-                    int lo = 0, hi = chunk_n - 1;   // last entry e with s_off[e] <= p (zero-length rows are skipped)
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (s_off[mid] <= p) lo = mid;
-                        else hi = mid - 1;
-                    }
+                    while (s_off[lo + 1] <= p) lo++;
                     const int64_t q = s_bs[lo] + (p - s_off[lo]);
                     jj[u] = Bj[q];
                     if (NUMERIC && sr.reads_b()) bb[u] = Bx[q];
                     if (NUMERIC && sr.reads_a()) aa[u] = s_av[lo];
                 }
+                p += 32;
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
@@ -424,6 +468,270 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         }
     } else {
         if (wlane == 0 && local_new) atomicAdd(&s_count, local_new);
+        __syncthreads();
+        if (tid == 0) row_nnz[row] = s_count;
+    }
+}
+
+// ------------------------------------------------------------------ numeric kernels without shared-memory atomics
+// A shared-memory atomic costs ~2 SM cycles per lane on sm_100 (64 cycles per warp instruction, whatever the addresses), which
+// made the atomicCAS of the hash insert the limiter of the numeric phase: products arrive faster than one CAS per product
+// can retire.  Most products of a sparse product open a NEW slot (nnz(C) ~ flops), so the claim is done with plain loads and
+// stores instead, in rounds of one product per thread separated by warp / CTA barriers:
+//   probe   every thread walks its probe sequence on the table as it stood at the barrier (nobody writes keys now): a slot
+//           with its key -> combine into the (final) value and done; the first EMPTY slot -> candidate;
+//   elect   candidates store a tag -(thread id + 2) into the KEY word of their slot -- exactly one tag survives;
+//   own     the thread that reads back its own tag owns the slot: it stores the value, then the real key (tags are < -1,
+//           keys are >= 0, so a slower candidate reading the word meanwhile can never mistake either for its own tag);
+//   settle  the others re-read the key: same key -> atomic combine (rare), other key -> probe on from the next slot next round.
+// Threads holding the same key compute the same candidate from the same snapshot, so a key can never occupy two slots;
+// every tag is replaced by its winner's key before the next probe phase, so probes only ever see EMPTY or real keys.
+__device__ __forceinline__ void elect_store(int *slot, int tag) { *reinterpret_cast<volatile int *>(slot) = tag; }
+__device__ __forceinline__ int elect_load(const int *slot) { return *reinterpret_cast<const volatile int *>(slot); }
+
+template <typename T> static __host__ __device__ inline size_t warp_elect_bytes(int cap) {
+    // s_bs[32] (8 B) | vals[cap] | s_av[32] | keys[cap] | s_off[36]
+    return ((size_t)32 * 8 + (size_t)(cap + 32) * sizeof(T) + (size_t)(cap + 36) * 4 + 15) & ~(size_t)15;
+}
+
+template <typename SR, typename T>
+__global__ void __launch_bounds__(128)
+spgemm_warp_elect_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+                         const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                         const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                         int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (g >= n_rows) return;   // warps are independent: no CTA-wide barrier in this kernel
+    unsigned char *base = s_raw + warp_elect_bytes<T>(cap) * wib;
+    int64_t *s_bs = reinterpret_cast<int64_t *>(base);
+    T *vals = reinterpret_cast<T *>(s_bs + 32);
+    T *s_av = vals + cap;
+    int *keys = reinterpret_cast<int *>(s_av + 32);
+    int *s_off = keys + cap;
+    const int64_t row = rows[g];
+    const unsigned tsize = (unsigned)table_size_for(cnt[row], cap, tf8);
+    for (unsigned t = lane; t < tsize; t += 32) keys[t] = HASH_EMPTY;
+    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
+    for (int64_t c0 = a_beg; c0 < a_end; c0 += 32) {
+        __syncwarp();   // table init / the previous chunk's readers of s_*
+        int len = 0;
+        if (c0 + lane < a_end) {
+            const int64_t k = c0 + lane;
+            const int32_t br = Aj[k];
+            const int64_t bs = Bp[br];
+            len = (int)(Bp[br + 1] - bs);
+            s_bs[lane] = bs;
+            if (sr.reads_a()) s_av[lane] = Ax[k];
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        s_off[lane] = incl - len;
+        if (lane == 31) s_off[32] = incl;
+        __syncwarp();
+        const int P = s_off[32];
+        int lo = 0;   // products of a lane only move forward, so the owning A entry is found by walking, never by searching
+        for (int base0 = 0; base0 < P; base0 += 32 * UNROLL) {
+            int jj[UNROLL];
+            T bb[UNROLL], aa[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const int pp = base0 + u * 32 + lane;
+                jj[u] = HASH_EMPTY;
+                if (pp < P) {
+                    while (s_off[lo + 1] <= pp) lo++;
+                    const int64_t q = s_bs[lo] + (pp - s_off[lo]);
+                    jj[u] = Bj[q];
+                    if (sr.reads_b()) bb[u] = Bx[q];
+                    if (sr.reads_a()) aa[u] = s_av[lo];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (base0 + u * 32 >= P) break;   // uniform
+                const int j = jj[u];
+                bool have = j != HASH_EMPTY;
+                const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                unsigned h = have ? hash_slot(j, tsize) : 0u;
+                while (true) {
+                    bool claim = false;
+                    if (have) {
+                        int k = keys[h];
+                        while (k != HASH_EMPTY && k != j) {
+                            h = (h + 1 == tsize) ? 0 : h + 1;
+                            k = keys[h];
+                        }
+                        if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                        else claim = true;
+                    }
+                    if (!__any_sync(FULL, claim)) break;
+                    __syncwarp();   // every probe of this round has read its keys
+                    if (claim) elect_store(&keys[h], -(lane + 2));
+                    __syncwarp();
+                    if (claim && elect_load(&keys[h]) == -(lane + 2)) {
+                        vals[h] = pr;
+                        elect_store(&keys[h], j);
+                        have = false;
+                        claim = false;
+                    }
+                    __syncwarp();
+                    if (claim) {   // lost the slot: to the same key (combine) or to another one (probe on next round)
+                        if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                        else h = (h + 1 == tsize) ? 0 : h + 1;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // drain: ballot compaction, no atomics
+    const int64_t ob = Op[row];
+    int outpos = 0;
+    for (unsigned t0 = 0; t0 < tsize; t0 += 32) {
+        const unsigned t = t0 + lane;
+        const int key = t < tsize ? keys[t] : HASH_EMPTY;
+        const unsigned m = __ballot_sync(FULL, key >= 0);
+        if (key >= 0) {
+            const int pos = outpos + __popc(m & ((1u << lane) - 1u));
+            Oj[ob + pos] = key;
+            Ox[ob + pos] = vals[t];
+        }
+        outpos += __popc(m);
+    }
+    if (lane == 0 && row_nnz) row_nnz[row] = outpos;
+}
+
+static inline size_t block_elect_bytes(int cap, int threads, size_t val_bytes) {
+    return (((size_t)cap * (val_bytes + 4) + 15) & ~(size_t)15) + block_stage_bytes(threads, val_bytes);
+}
+
+template <typename SR, typename T>
+__global__ void spgemm_block_elect_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+                                          const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                                          const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                                          int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
+                                          T *__restrict__ Ox) {
+    // dynamic shared memory: vals[cap] | keys[cap] | s_bs[nthreads] | s_off[nthreads + 1 ..] | s_av[nthreads]
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_wsum[MAX_THREADS / 32];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    T *vals = reinterpret_cast<T *>(s_raw);
+    int *keys = reinterpret_cast<int *>(vals + cap);
+    int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + ((((size_t)cap * (sizeof(T) + 4)) + 15) & ~(size_t)15));
+    int *s_off = reinterpret_cast<int *>(s_bs + nthreads);
+    T *s_av = reinterpret_cast<T *>(s_off + ((nthreads + 4) & ~3));
+    const int64_t row = rows[blockIdx.x];
+    const unsigned tsize = (unsigned)table_size_for(cnt[row], cap, tf8);
+    for (unsigned t = tid; t < tsize; t += nthreads) keys[t] = HASH_EMPTY;
+    if (tid == 0) s_count = 0;
+
+    const int wlane = tid & 31, warp = tid >> 5;
+    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
+    for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
+        const int chunk_n = (int)((a_end - c0 < nthreads) ? (a_end - c0) : nthreads);
+        int len = 0;
+        if (tid < chunk_n) {
+            const int64_t k = c0 + tid;
+            const int32_t br = Aj[k];
+            const int64_t bs = Bp[br];
+            len = (int)(Bp[br + 1] - bs);
+            s_bs[tid] = bs;
+            if (sr.reads_a()) s_av[tid] = Ax[k];
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (wlane >= o) incl += up;
+        }
+        if (wlane == 31) s_wsum[warp] = incl;
+        __syncthreads();   // also orders the table init / the previous chunk's rounds before this chunk's
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_wsum[w];
+        s_off[tid] = base + incl - len;
+        if (tid == nthreads - 1) s_off[nthreads] = base + incl;
+        __syncthreads();
+        const int P = s_off[nthreads];
+        for (int base0 = 0; base0 < P; base0 += nthreads * UNROLL) {   // trip counts are uniform over the CTA (barriers inside)
+            int jj[UNROLL];
+            T bb[UNROLL], aa[UNROLL];
+            int pp = base0 + warp * (32 * UNROLL) + wlane;
+            int lo = 0;
+            if (pp < P) {
+                int hi = chunk_n - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= pp) lo = mid;
+                    else hi = mid - 1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                jj[u] = HASH_EMPTY;
+                if (pp < P) {
+                    while (s_off[lo + 1] <= pp) lo++;
+                    const int64_t q = s_bs[lo] + (pp - s_off[lo]);
+                    jj[u] = Bj[q];
+                    if (sr.reads_b()) bb[u] = Bx[q];
+                    if (sr.reads_a()) aa[u] = s_av[lo];
+                }
+                pp += 32;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (base0 + u * 32 >= P) break;   // uniform: no thread of the CTA has a product in this slot
+                const int j = jj[u];
+                bool have = j != HASH_EMPTY;
+                const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                unsigned h = have ? hash_slot(j, tsize) : 0u;
+                while (true) {
+                    bool claim = false;
+                    if (have) {
+                        int k = keys[h];
+                        while (k != HASH_EMPTY && k != j) {
+                            h = (h + 1 == tsize) ? 0 : h + 1;
+                            k = keys[h];
+                        }
+                        if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                        else claim = true;
+                    }
+                    if (!__syncthreads_or(claim)) break;   // barrier: every probe of this round has read its keys
+                    if (claim) elect_store(&keys[h], -(tid + 2));
+                    __syncthreads();
+                    if (claim && elect_load(&keys[h]) == -(tid + 2)) {
+                        vals[h] = pr;
+                        elect_store(&keys[h], j);
+                        have = false;
+                        claim = false;
+                    }
+                    __syncthreads();
+                    if (claim) {
+                        if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                        else h = (h + 1 == tsize) ? 0 : h + 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // s_* arrays are rewritten by the next chunk
+    }
+    __syncthreads();
+    const int64_t ob = Op[row];
+    for (unsigned t = tid; t < tsize; t += nthreads) {
+        const int key = keys[t];
+        if (key >= 0) {
+            const int pos = atomicAdd(&s_count, 1);   // warp-aggregated by the compiler
+            Oj[ob + pos] = key;
+            Ox[ob + pos] = vals[t];
+        }
+    }
+    if (row_nnz) {
         __syncthreads();
         if (tid == 0) row_nnz[row] = s_count;
     }
@@ -476,11 +784,23 @@ compact_rows_kernel(int64_t nrows, const int64_t *__restrict__ Sp, const int64_t
     for (int64_t i = w; i < nrows; i += nw) {
         const int64_t src = Sp[i], dst = Cp[i], n = Cp[i + 1] - dst;
         int64_t k = lane;
+        for (; k + 224 < n; k += 256) {   // 16 independent loads in flight per lane: the copy is latency x bytes-in-flight bound
+            int32_t j[8];
+            T x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) j[u] = __ldcs(Sj + src + k + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = __ldcs(Sx + src + k + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) __stcs(Cj + dst + k + 32 * u, j[u]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) __stcs(Cx + dst + k + 32 * u, x[u]);
+        }
         for (; k + 96 < n; k += 128) {
             int32_t j0 = __ldcs(Sj + src + k), j1 = __ldcs(Sj + src + k + 32), j2 = __ldcs(Sj + src + k + 64), j3 = __ldcs(Sj + src + k + 96);
             T x0 = __ldcs(Sx + src + k), x1 = __ldcs(Sx + src + k + 32), x2 = __ldcs(Sx + src + k + 64), x3 = __ldcs(Sx + src + k + 96);
-            Cj[dst + k] = j0; Cj[dst + k + 32] = j1; Cj[dst + k + 64] = j2; Cj[dst + k + 96] = j3;
-            Cx[dst + k] = x0; Cx[dst + k + 32] = x1; Cx[dst + k + 64] = x2; Cx[dst + k + 96] = x3;
+            __stcs(Cj + dst + k, j0); __stcs(Cj + dst + k + 32, j1); __stcs(Cj + dst + k + 64, j2); __stcs(Cj + dst + k + 96, j3);
+            __stcs(Cx + dst + k, x0); __stcs(Cx + dst + k + 32, x1); __stcs(Cx + dst + k + 64, x2); __stcs(Cx + dst + k + 96, x3);
         }
         for (; k < n; k += 32) {
             Cj[dst + k] = __ldcs(Sj + src + k);
@@ -547,6 +867,31 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
         if (n == 0) continue;
         const int32_t *rows = bins.rows + bins.start[b];
         const int cap = bins.spec.cap[b], threads = bins.spec.threads[b];
+        if constexpr (NUMERIC && sizeof(T) >= 4) {
+            // atomics-free owner-election kernels (see above): unmasked numeric products with shared-memory tables
+            if (!a.mk.Mp && b < NBINS - 1 && (bins.spec.flags & 2) && b >= (int)opt_get_int("spgemm_elect_from_bin", 1) &&
+                b <= (int)opt_get_int("spgemm_elect_to_bin", NBINS)) {
+                const bool warp_rows = b <= 2 || (size_t)cap * (sizeof(T) + 4) <= (size_t)opt_get_int("spgemm_warp_table_bytes", 16384);
+                if (warp_rows) {
+                    const int rpb = 4;
+                    const size_t smem = warp_elect_bytes<T>(cap) * rpb;
+                    auto kern = spgemm_warp_elect_kernel<SR, T>;
+                    if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    LAUNCH_NOTE("spgemm_numeric_warp");
+                    kern<<<(unsigned)((n + rpb - 1) / rpb), 32 * rpb, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+                } else {
+                    const size_t smem = block_elect_bytes(cap, threads, sizeof(T));
+                    auto kern = spgemm_block_elect_kernel<SR, T>;
+                    CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                    LAUNCH_NOTE("spgemm_numeric_block");
+                    kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+                }
+                cudaError_t le = cudaGetLastError();
+                if (le != cudaSuccess)
+                    return set_error(err, GrB_PANIC, "spgemm elect kernel launch failed in bin %d (cap %d, %d threads, %lld rows): %s", b, cap, threads, (long long)n, cudaGetErrorString(le));
+                continue;
+            }
+        }
         if (b <= 2) {
             const int rpb = threads / 32;
             const size_t per = (((size_t)cap * entry + 8) + 15) & ~(size_t)15;
@@ -554,13 +899,13 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             auto kern = spgemm_warp_kernel<SR, T, NUMERIC, PACK>;
             if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
-            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
+            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
         } else if (b < NBINS - 1) {
-            const size_t smem = (size_t)cap * entry;
+            const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
-            CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));   // static + dynamic may exceed 48 KB in any bin
+            CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
-            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
+            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
@@ -588,7 +933,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 if (!info) {
                     cudaMemcpyAsync(doffs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, g_stream);
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, 0, g_stream>>>(sr, rows + i0, 0, bins.spec.tf8, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows + i0, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
                     cudaStreamSynchronize(g_stream);   // offs is host memory
                 }
                 dev_free(doffs); dev_free(gt);
@@ -663,6 +1008,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     const int D = op ? op->type : TC_INT64;
     const size_t es = type_size(D);
 
+    phase_mark(nullptr);
     int64_t *flops = dev_alloc_t<int64_t>((size_t)p.m + 1), *row_nnz = dev_alloc_t<int64_t>((size_t)p.m + 1);
     int64_t *Sp = nullptr;
     int32_t *Sj = nullptr;
@@ -693,6 +1039,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     }
     const uint64_t total_flops = hred[0];
     if (flops_out) *flops_out = total_flops;
+    phase_mark("mxm_row_flops");
 
     // one pass (no symbolic phase) when the flops-sized staging copy plus the result fit comfortably
     bool onepass = false;
@@ -735,7 +1082,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         if (!info) {
             BinSpec spec = make_bin_spec(entry);
             note_launch("masked_count");
-            masked_count_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, M->csr.ptr, spec.maxcount[9], mcnt);
+            masked_count_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, M->csr.ptr, spec.maxcount[BIN_LAST_SHARED], mcnt);
             info = make_bins(&fbins, entry, p.m, mcnt, err);
         }
         if (!info) {
@@ -779,7 +1126,9 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         // ---- bins and tables from the flops bound; staging addressed by the flops prefix
         size_t entry = 12;
         GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
+        phase_mark("mxm_plan");
         info = make_bins(&fbins, entry, p.m, flops, err);
+        phase_mark("mxm_bins");
         if (!info) {
             Sp = dev_alloc_t<int64_t>((size_t)p.m + 1);
             Sj = (int32_t *)ws_acquire(0, (size_t)total_flops * 4);
@@ -793,19 +1142,23 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         }
         if (!info) {
             GrB_Info i3 = GrB_NOT_IMPLEMENTED;
+            phase_mark("mxm_staging_alloc");
             GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, flops, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err));
             info = i3;
+            phase_mark("mxm_numeric_launch");
         }
         if (!info) {
             note_launch("i64_copy");
             i64_copy_kernel<<<copy_blocks, 256, 0, g_stream>>>(Tm->csr.ptr, row_nnz, p.m + 1);
             info = exclusive_scan_i64(Tm->csr.ptr, p.m + 1, err);
             if (!info) total = read_i64(Tm->csr.ptr + p.m);
+            phase_mark("mxm_numeric_wait");
         }
         if (!info) {
             size_t nv = (size_t)(total > 0 ? total : 1);
             Tm->csr.idx = dev_alloc_t<int32_t>(nv);
             Tm->csr.val = dev_alloc(nv * es);
+            phase_mark("mxm_result_alloc");
             Tm->nvals = total;
             Tm->jumbled = true;
             if (!Tm->csr.idx || !Tm->csr.val) info = set_error(err, GrB_OUT_OF_MEMORY, "mxm result needs %lld entries (%.1f GB)", (long long)total, (double)total * (4 + es) / 1e9);
@@ -855,6 +1208,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         }
     }
     if (nvals_out) *nvals_out = (uint64_t)total;
+    phase_mark("mxm_compact_launch");
     dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(fbins.rows); dev_free(nbins.rows);
     dev_free(Sp); ws_release(0, Sj); ws_release(1, Sx);
     if (info || symbolic_only) {
@@ -862,5 +1216,6 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         return info;
     }
     *Tout = Tm;
+    phase_mark("mxm_free");
     return GrB_SUCCESS;
 }

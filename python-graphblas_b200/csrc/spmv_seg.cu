@@ -483,7 +483,24 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
     size_t smem_total = (size_t)opt_get_int("spmv_hot_kb", 132) * 1024 - 1024;
     if (smem_total > (size_t)SEG_SMEM_BYTES) smem_total = SEG_SMEM_BYTES;
     const size_t hot_budget = smem_total > stage_bytes ? smem_total - stage_bytes : 0;
-    const int hot_k = SR::kStatic ? seg_hot_plan(M, ncols, nnz, sizeof(T), hot_budget, xp == nullptr, sr.reads_b(), err) : 0;
+    int hot_k = SR::kStatic ? seg_hot_plan(M, ncols, nnz, sizeof(T), hot_budget, xp == nullptr, sr.reads_b(), err) : 0;
+    // auto mode: whether the cache pays depends on how the labels are laid out (on natural R-MAT labels the hot columns
+    // are neighbours and L1 already serves them; on permuted labels the cache wins ~15 %), so the first two multiplies
+    // that could use it are a timed trial -- plain kernel, then hot kernel -- and the winner is kept for this CSR.
+    int trial = 0;
+    if (hot_k && !strcmp(opt_get("spmv_hot", "auto"), "auto")) {
+        if (M.hot_choice == 1) hot_k = 0;
+        else if (M.hot_choice == 0) {
+            trial = M.hot_trial_ms < 0.f ? 1 : 2;
+            if (trial == 1) hot_k = 0;
+        }
+    }
+    static cudaEvent_t trial_ev[2] = {nullptr, nullptr};
+    if (trial) {
+        for (int q = 0; q < 2; q++)
+            if (!trial_ev[q] && cudaEventCreate(&trial_ev[q]) != cudaSuccess) { trial = 0; break; }
+        if (!trial) { (void)cudaGetLastError(); if (M.hot_choice == 0 && M.hot_trial_ms < 0.f) hot_k = 0; }
+    }
     const int32_t *cols = hot_k ? M.hot_remap : M.idx;
 
     constexpr int TILE = SegCfg<T>::TILE;
@@ -511,6 +528,7 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
         bd.tail_has = q;
     }
     cudaError_t e = cudaSuccess;
+    if (trial) cudaEventRecord(trial_ev[0], g_stream);
     if (hot_k) {
         LAUNCH_NOTE("spmv_hot_gather");
         seg_hot_gather_kernel<T><<<(hot_k + 255) / 256, 256, 0, g_stream>>>(sr.reads_b() ? x : nullptr, xp, M.hot_cols, hot_k, xhot, xhotp);
@@ -546,6 +564,17 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
         seg_fixup_kernel<SR, T><<<(unsigned)((n_warps + 1 + 255) / 256), 256, 0, g_stream>>>(sr, n_warps, M.seg_rows, bd, t_vals, t_present, epi);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
+    if (trial && e == cudaSuccess) {
+        float ms = 0.f;
+        cudaEventRecord(trial_ev[1], g_stream);
+        if (cudaEventSynchronize(trial_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, trial_ev[0], trial_ev[1]) == cudaSuccess) {
+            if (trial == 1) M.hot_trial_ms = ms;
+            else M.hot_choice = ms < M.hot_trial_ms ? 2 : 1;
+        } else {
+            (void)cudaGetLastError();
+            M.hot_choice = 1;
+        }
+    }
     dev_free(brec); dev_free(xhot); dev_free(xhotp);
     CUDA_TRY(err, e);
     return GrB_SUCCESS;

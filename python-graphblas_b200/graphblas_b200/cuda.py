@@ -201,6 +201,32 @@ def vector_as_torch(v, sync=True):
     return vals, pres
 
 
+def matrix_as_torch(A, sync=True):
+    """zero-copy torch views (indptr int64, col_indices int32, values) of the matrix's device CSR (GrB_cuda_Matrix_device_csr).
+    Rows may be unsorted after mxm -- call matrix_sort(A) first when order matters.  Read-only; valid until A changes."""
+    import torch
+
+    ap, aj, ax = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    call("GrB_cuda_Matrix_device_csr", [A, ctypes.byref(ap), ctypes.byref(aj), ctypes.byref(ax)])
+    if sync:
+        globals()["sync"]()
+    else:
+        _torch_waits()
+    nv = A.nvals
+    indptr = torch.as_tensor(_CudaArray(ap.value, (A.nrows + 1,), "<i8"), device="cuda")
+    if nv == 0:
+        return indptr, torch.empty(0, dtype=torch.int32, device="cuda"), torch.empty(0, dtype=_torch_dtype_of(A.dtype), device="cuda")
+    cols = torch.as_tensor(_CudaArray(aj.value, (nv,), "<i4"), device="cuda")
+    vals = torch.as_tensor(_CudaArray(ax.value, (nv,), np.dtype(A.dtype.np_type).str if A.dtype.name != "BOOL" else "|u1"), device="cuda")
+    return indptr, cols, vals
+
+
+def _torch_dtype_of(dtype):
+    import torch
+
+    return torch.uint8 if dtype.name == "BOOL" else getattr(torch, np.dtype(dtype.np_type).name)
+
+
 def vector_touch(v):
     call("GrB_cuda_Vector_touch", [v])
 
