@@ -213,6 +213,9 @@ GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void *Ax, GrB_In
                                       GrB_Matrix A, int sort);
 /* raw device views (valid until the object is next modified) */
 GrB_Info GrB_cuda_Matrix_device_csr(const GrB_Matrix A, int64_t **Ap, int32_t **Aj, void **Ax);
+/* v as an n x 1 matrix (column vector), built on the device: what Vector._as_matrix provides for Vector.inner / Vector.outer
+   (reference graphblas/core/vector.py:193-209, 1715-1787) */
+GrB_Info GrB_cuda_Matrix_from_Vector(GrB_Matrix *A, const GrB_Vector v);
 GrB_Info GrB_cuda_Vector_device_arrays(const GrB_Vector v, void **vals, uint8_t **present);
 GrB_Info GrB_cuda_Vector_import_dense(GrB_Vector *v, GrB_Type type, GrB_Index n, const void *vals,
                                       const uint8_t *present /* NULL = full */, int on_device);

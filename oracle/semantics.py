@@ -296,3 +296,19 @@ def vxm(w, m, accum, semiring, u, A, *, t1=False, complement=False, structure=Fa
     mxm(Cm, None if m is None else m.as_row(), accum, semiring, u.as_row(), A, t1=t1,
         complement=complement, structure=structure, replace=replace)
     return _vec_from_mat(w, Cm, 1)
+
+
+def inner(semiring, u, v):
+    """Vector.inner -- reference core/vector.py:1715-1744: GrB_vxm of u against v cast to an n x 1 matrix; the single entry of
+    the 1-vector result, or None when u and v share no index.  Returns (value, dtype)."""
+    if u.size != v.size:
+        raise ValueError("GrB_DIMENSION_MISMATCH")
+    T, D = _multiply(u.as_row(), v.as_col(), semiring)
+    return (T.get((0, 0)), D)
+
+
+def outer(binop, u, v):
+    """Vector.outer -- reference core/vector.py:1746-1787: GrB_mxm(any_<binop>) of u as n x 1 and v as 1 x m (GrB_DESC_T1 on the
+    column form).  Returns an SpMat."""
+    T, D = _multiply(u.as_col(), v.as_row(), f"any_{binop}")
+    return SpMat(u.size, v.size, D, T)

@@ -52,8 +52,11 @@ struct CsrArrays {
     int hot_n = 0;
     int hot_state = 0;               // 0 not analysed, 1 built, -1 not worthwhile
     int pull_calls = 0;              // pull SpMV calls seen (the analysis is paid for on the second one)
-    int hot_choice = 0;              // auto mode: 0 undecided, 1 plain kernel won the timed trial, 2 hot-column kernel won
-    float hot_trial_ms = -1.f;       // auto mode: time of the plain kernel in the trial (< 0: not yet run)
+    // auto mode of the pull SpMV (spmv.cu run_pull): timed trial of merge-path / segmented / segmented + hot-column cache on the
+    // first multiplies with this CSR, per element-size class (<= 4 bytes, 8 bytes); the winner is kept
+    int pull_choice[2] = {0, 0};     // 0 undecided, 1 merge, 2 seg, 3 seg + hot columns
+    int pull_stage[2] = {0, 0};      // next candidate to time
+    float pull_ms[2][3] = {{-1.f, -1.f, -1.f}, {-1.f, -1.f, -1.f}};
     // row-boundary metadata of the segmented pull SpMV (spmv_seg.cu), built on first use
     uint8_t *seg_flags = nullptr;    // bit (k & 7) of byte (k >> 3): entry k is the first of its row
     int32_t *seg_rows = nullptr;     // rows that have at least one entry, ascending

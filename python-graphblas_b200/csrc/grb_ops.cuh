@@ -34,8 +34,8 @@ template <> __host__ __device__ __forceinline__ gbool one_of<gbool>() { return g
 template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T y) {
     if constexpr (is_gbool<T>::value) {
         switch (op) {
-            case OP_FIRST: case OP_ANY: case OP_DIV: return x;
-            case OP_SECOND: case OP_RDIV: return y;
+            case OP_FIRST: case OP_DIV: return x;
+            case OP_SECOND: case OP_RDIV: case OP_ANY: return y;   // any(x, y) may return either; y makes any(identity, p) = p
             case OP_PAIR: return gbool(true);
             case OP_PLUS: case OP_LOR: case OP_MAX: return gbool(x.v | y.v);
             case OP_TIMES: case OP_LAND: case OP_MIN: return gbool(x.v & y.v);
@@ -49,8 +49,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
         return x;
     } else if constexpr (std::is_floating_point<T>::value) {
         switch (op) {
-            case OP_FIRST: case OP_ANY: return x;
-            case OP_SECOND: return y;
+            case OP_FIRST: return x;
+            case OP_SECOND: case OP_ANY: return y;   // any(x, y) may return either; y makes any(identity, p) = p
             case OP_PAIR: return (T)1;
             case OP_PLUS: return x + y;
             case OP_MINUS: return x - y;
@@ -71,8 +71,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
     } else {
         typedef typename std::make_unsigned<T>::type U;   // wrap-around arithmetic
         switch (op) {
-            case OP_FIRST: case OP_ANY: return x;
-            case OP_SECOND: return y;
+            case OP_FIRST: return x;
+            case OP_SECOND: case OP_ANY: return y;   // any(x, y) may return either; y makes any(identity, p) = p
             case OP_PAIR: return (T)1;
             case OP_PLUS: return (T)((U)x + (U)y);
             case OP_MINUS: return (T)((U)x - (U)y);

@@ -612,3 +612,55 @@ extern "C" GrB_Info GrB_cuda_Vector_export_dense(void *vals, uint8_t *present, c
     CUDA_TRY(&v->err, cudaStreamSynchronize(g_stream));
     return GrB_SUCCESS;
 }
+
+// ------------------------------------------------------------------ vector -> n x 1 matrix (column vector)
+// The reference's Vector.inner / Vector.outer run GrB_vxm / GrB_mxm on the vector "cast" to a matrix
+// (graphblas/core/vector.py:193-209 `_as_matrix`, :1715-1787); on the vanilla backend that is a fresh n x 1 Matrix filled by
+// a column assign.  Here: presence bytes -> row pointers (exclusive scan), values compacted, every column index 0.
+__global__ void vec_present_to_counts_kernel(int64_t n, const uint8_t *__restrict__ present, int64_t *__restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= n; i += s) cnt[i] = (i < n && present[i]) ? 1 : 0;
+}
+__global__ void vec_to_column_kernel(int64_t n, const uint8_t *__restrict__ present, const unsigned char *__restrict__ vals,
+                                     size_t es, const int64_t *__restrict__ ptr, int32_t *__restrict__ idx,
+                                     unsigned char *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += s) {
+        if (!present[i]) continue;
+        const int64_t k = ptr[i];
+        idx[k] = 0;
+        for (size_t b = 0; b < es; b++) out[(size_t)k * es + b] = vals[(size_t)i * es + b];
+    }
+}
+
+extern "C" GrB_Info GrB_cuda_Matrix_from_Vector(GrB_Matrix *Aout, const GrB_Vector v) {
+    CHECK_INIT();
+    if (!Aout) return GrB_NULL_POINTER;
+    if (!valid(v)) return GrB_UNINITIALIZED_OBJECT;
+    GRB_TRY(vector_ensure_arrays(v));
+    GRB_TRY(vector_count(v));
+    GrB_Matrix A = nullptr;
+    GRB_TRY(matrix_new_shell(&A, v->type, v->n, 1));
+    GrB_Info info = matrix_alloc_csr(A, v->nvals);
+    if (!info) {
+        const int blocks = (int)std::min<int64_t>((v->n + 256) / 256, (int64_t)g_num_sms * 16);
+        note_launch("vec_present_to_counts");
+        vec_present_to_counts_kernel<<<blocks, 256, 0, g_stream>>>(v->n, v->present, A->csr.ptr);
+        info = exclusive_scan_i64(A->csr.ptr, v->n + 1, &A->err);
+    }
+    if (!info && v->nvals > 0) {
+        const int blocks = (int)std::min<int64_t>((v->n + 255) / 256, (int64_t)g_num_sms * 16);
+        note_launch("vec_to_column");
+        vec_to_column_kernel<<<blocks, 256, 0, g_stream>>>(v->n, v->present, (const unsigned char *)v->vals, type_size(v->type),
+                                                           A->csr.ptr, A->csr.idx, (unsigned char *)A->csr.val);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) info = cuda_fail(&A->err, e, "vector to column matrix");
+    }
+    if (info) { set_last_error(A->err.c_str()); GrB_Matrix_free(&A); return info; }
+    A->nvals = v->nvals;
+    A->jumbled = false;
+    *Aout = A;
+    return GrB_SUCCESS;
+}

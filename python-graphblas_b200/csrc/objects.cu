@@ -41,8 +41,11 @@ void csr_drop_hot(CsrArrays &c) {
     c.hot_n = 0;
     c.hot_state = 0;
     c.pull_calls = 0;
-    c.hot_choice = 0;
-    c.hot_trial_ms = -1.f;
+    for (int q = 0; q < 2; q++) {
+        c.pull_choice[q] = 0;
+        c.pull_stage[q] = 0;
+        for (int k = 0; k < 3; k++) c.pull_ms[q][k] = -1.f;
+    }
 }
 
 void csr_drop_seg(CsrArrays &c) {

@@ -381,11 +381,68 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
         CUDA_TRY(err, cudaGetLastError());
         return GrB_SUCCESS;
     }
-    if (!strcmp(method, "auto") || !strcmp(method, "seg")) {   // default: segmented kernel (spmv_seg.cu)
-        bool handled = false;
+    // ---- which pull kernel.  Explicit options pick one; "auto" keeps the fused write-back on the merge-path kernel (its
+    // per-row emission is coalesced; the segmented kernel emits row by row) and otherwise settles the choice between
+    // merge-path / segmented / segmented + hot-column cache by a timed trial on the first multiplies with this CSR:
+    // which one wins depends on the value width and on how the labels are laid out (natural R-MAT labels keep the hot
+    // columns adjacent, so L1 already serves them; permuted labels make the shared-memory cache win by ~15 %).
+    int candidate = 1;   // 1 merge, 2 seg, 3 seg + hot columns
+    int trial_cls = -1;
+    static cudaEvent_t trial_ev[2] = {nullptr, nullptr};
+    if (!strcmp(method, "seg")) candidate = 2;
+    else if (!strcmp(method, "auto") && !epi.active) {
+        const int cls = sizeof(T) >= 8 ? 1 : 0;
+        candidate = cls ? 2 : 1;
+        const char *hot_opt = opt_get("spmv_hot", "auto");
+        if (!strcmp(hot_opt, "1")) candidate = 2;   // forced cache: segmented kernel, spmv_seg_run honours the option
+        else if (SR::kStatic && nnz >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_trial", 1) != 0) {
+            if (M.pull_choice[cls]) candidate = M.pull_choice[cls];
+            else {
+                candidate = 1 + M.pull_stage[cls] / 2;   // every candidate runs twice: once to set up its cached metadata, once timed
+                if (candidate == 3 && !strcmp(hot_opt, "0")) {   // cache switched off: decide between the first two now
+                    M.pull_choice[cls] = M.pull_ms[cls][1] < M.pull_ms[cls][0] ? 2 : 1;
+                    candidate = M.pull_choice[cls];
+                } else {
+                    trial_cls = cls;
+                    if ((M.pull_stage[cls] & 1) == 0) { M.pull_stage[cls]++; trial_cls = -1; }   // warm-up run, untimed
+                    for (int q = 0; q < 2 && trial_cls >= 0; q++)
+                        if (!trial_ev[q] && cudaEventCreate(&trial_ev[q]) != cudaSuccess) {
+                            (void)cudaGetLastError();
+                            trial_cls = -1;
+                            M.pull_choice[cls] = candidate = cls ? 2 : 1;   // cannot time: keep the static default
+                        }
+                    if (trial_cls >= 0) cudaEventRecord(trial_ev[0], g_stream);
+                }
+            }
+        }
+    }
+    auto finish_trial = [&](int ran) {   // `ran`: the candidate that actually executed
+        if (trial_cls < 0) return;
+        float ms = 0.f;
+        cudaEventRecord(trial_ev[1], g_stream);
+        if (cudaEventSynchronize(trial_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, trial_ev[0], trial_ev[1]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            M.pull_choice[trial_cls] = trial_cls ? 2 : 1;
+            return;
+        }
+        const int stage = M.pull_stage[trial_cls] / 2;
+        M.pull_ms[trial_cls][stage] = (stage == 2 && ran != 3) ? 1e30f : ms;   // cache not viable: candidate 3 cannot win
+        if (++M.pull_stage[trial_cls] == 6) {
+            int best = 0;
+            for (int k = 1; k < 3; k++)
+                if (M.pull_ms[trial_cls][k] < M.pull_ms[trial_cls][best]) best = k;
+            M.pull_choice[trial_cls] = best + 1;
+        }
+    };
+    if (candidate >= 2) {
+        bool handled = false, used_hot = false;
+        const int hot_mode = !strcmp(method, "seg") || !strcmp(opt_get("spmv_hot", "auto"), "1") ? -1 : (candidate == 3 ? 1 : 0);
         GRB_TRY(spmv_seg_run(type_code_of<T>(), sr.add_op(), sr.mul_op(), M, mrows, x_len, nnz, avals, x, xp, t_vals, t_present,
-                             &epi, err, &handled));
-        if (handled) return GrB_SUCCESS;
+                             &epi, err, &handled, hot_mode, &used_hot));
+        if (handled) {
+            finish_trial(used_hot ? 3 : 2);
+            return GrB_SUCCESS;
+        }
     }
     constexpr int TILE = SPMV_BLOCK * SpmvCfg<T>::IPT;
     GRB_TRY(ensure_tiles(M, mrows, nnz, TILE, err));
@@ -409,6 +466,7 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
     cudaError_t e = cudaGetLastError();
     dev_free(carry_row); dev_free(carry_val); dev_free(carry_has);
     CUDA_TRY(err, e);
+    finish_trial(1);
     return GrB_SUCCESS;
 }
 

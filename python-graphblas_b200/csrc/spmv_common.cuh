@@ -85,6 +85,8 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
 
 // segmented pull SpMV (spmv_seg.cu).  Returns GrB_SUCCESS with *handled = false when the inputs do not fit the kernel
 // (unaligned arrays); the caller then falls back to the merge-path kernel.  `epi` may be null (plain T output).
+// hot_mode: -1 = follow option spmv_hot ("1" forces the hot-column cache), 0 = plain, 1 = hot-column cache when it is viable;
+// *used_hot reports whether the cache variant actually ran.
 GrB_Info spmv_seg_run(int type_code, int add_op, int mul_op, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz,
                       const void *avals, const void *x, const uint8_t *xp, void *t_vals, uint8_t *t_present,
-                      const void *epi_typed, std::string *err, bool *handled);
+                      const void *epi_typed, std::string *err, bool *handled, int hot_mode, bool *used_hot);

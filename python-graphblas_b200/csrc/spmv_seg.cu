@@ -434,15 +434,14 @@ __global__ void seg_hot_gather_kernel(const T *__restrict__ x, const uint8_t *__
 // ------------------------------------------------------------------ host side
 // number of hot ranks to keep in shared memory for this multiply (0 = plain kernel)
 static int seg_hot_plan(CsrArrays &M, int64_t ncols, int64_t nnz, size_t elem_bytes, size_t hot_budget, bool xfull, bool reads_b,
-                        std::string *err) {
+                        int hot_mode, std::string *err) {
     const char *mode = opt_get("spmv_hot", "auto");
-    if (!strcmp(mode, "0") || (!reads_b && xfull)) return 0;
-    const bool force = !strcmp(mode, "1");
-    M.pull_calls++;
+    if (hot_mode == 0 || (hot_mode < 0 && strcmp(mode, "1")) || (!reads_b && xfull)) return 0;   // off unless forced / asked for
+    const bool force = hot_mode < 0;   // option "1": no thresholds (tests); hot_mode 1: the caller's trial, thresholds apply
     const int max_ranks = SEG_SMEM_BYTES / 4;   // ranks kept in the remap: what a 4-byte table could ever hold
     if (M.hot_state == 0) {
-        // the analysis costs a few multiplies' worth of time: pay it on the second multiply with the same matrix
-        if (!force && (M.pull_calls < 2 || nnz < opt_get_int("spmv_hot_min_nnz", 1 << 20))) return 0;
+        // the analysis costs a few multiplies' worth of time: the caller's trial asks for it on the third multiply with this CSR
+        if (!force && nnz < opt_get_int("spmv_hot_min_nnz", 1 << 20)) return 0;
         if (csr_ensure_hot(M, ncols, nnz, max_ranks, err) != GrB_SUCCESS) return 0;
     }
     if (M.hot_state != 1 || M.hot_n == 0) return 0;
@@ -460,7 +459,7 @@ static int seg_hot_plan(CsrArrays &M, int64_t ncols, int64_t nnz, size_t elem_by
 template <typename SR, typename T>
 static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz, const T *avals, const T *x,
                               const uint8_t *xp, T *t_vals, uint8_t *t_present, const VecEpi<T> &epi, std::string *err,
-                              bool *handled) {
+                              bool *handled, int hot_mode, bool *used_hot) {
     *handled = false;
     if (mrows <= 0) { *handled = true; return GrB_SUCCESS; }
     // pre-fill: the result where T has no entry (every row for now; rows with entries are rewritten below)
@@ -483,25 +482,10 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
     size_t smem_total = (size_t)opt_get_int("spmv_hot_kb", 132) * 1024 - 1024;
     if (smem_total > (size_t)SEG_SMEM_BYTES) smem_total = SEG_SMEM_BYTES;
     const size_t hot_budget = smem_total > stage_bytes ? smem_total - stage_bytes : 0;
-    int hot_k = SR::kStatic ? seg_hot_plan(M, ncols, nnz, sizeof(T), hot_budget, xp == nullptr, sr.reads_b(), err) : 0;
-    // auto mode: whether the cache pays depends on how the labels are laid out (on natural R-MAT labels the hot columns
-    // are neighbours and L1 already serves them; on permuted labels the cache wins ~15 %), so the first two multiplies
-    // that could use it are a timed trial -- plain kernel, then hot kernel -- and the winner is kept for this CSR.
-    int trial = 0;
-    if (hot_k && !strcmp(opt_get("spmv_hot", "auto"), "auto")) {
-        if (M.hot_choice == 1) hot_k = 0;
-        else if (M.hot_choice == 0) {
-            trial = M.hot_trial_ms < 0.f ? 1 : 2;
-            if (trial == 1) hot_k = 0;
-        }
-    }
-    static cudaEvent_t trial_ev[2] = {nullptr, nullptr};
-    if (trial) {
-        for (int q = 0; q < 2; q++)
-            if (!trial_ev[q] && cudaEventCreate(&trial_ev[q]) != cudaSuccess) { trial = 0; break; }
-        if (!trial) { (void)cudaGetLastError(); if (M.hot_choice == 0 && M.hot_trial_ms < 0.f) hot_k = 0; }
-    }
+    int hot_k = SR::kStatic ? seg_hot_plan(M, ncols, nnz, sizeof(T), hot_budget, xp == nullptr, sr.reads_b(), hot_mode, err) : 0;
+    if (hot_mode == 0) hot_k = 0;
     const int32_t *cols = hot_k ? M.hot_remap : M.idx;
+    if (used_hot) *used_hot = hot_k > 0;
 
     constexpr int TILE = SegCfg<T>::TILE;
     const int64_t n_tiles = (nnz + TILE - 1) / TILE;
@@ -528,7 +512,6 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
         bd.tail_has = q;
     }
     cudaError_t e = cudaSuccess;
-    if (trial) cudaEventRecord(trial_ev[0], g_stream);
     if (hot_k) {
         LAUNCH_NOTE("spmv_hot_gather");
         seg_hot_gather_kernel<T><<<(hot_k + 255) / 256, 256, 0, g_stream>>>(sr.reads_b() ? x : nullptr, xp, M.hot_cols, hot_k, xhot, xhotp);
@@ -564,17 +547,6 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
         seg_fixup_kernel<SR, T><<<(unsigned)((n_warps + 1 + 255) / 256), 256, 0, g_stream>>>(sr, n_warps, M.seg_rows, bd, t_vals, t_present, epi);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (trial && e == cudaSuccess) {
-        float ms = 0.f;
-        cudaEventRecord(trial_ev[1], g_stream);
-        if (cudaEventSynchronize(trial_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, trial_ev[0], trial_ev[1]) == cudaSuccess) {
-            if (trial == 1) M.hot_trial_ms = ms;
-            else M.hot_choice = ms < M.hot_trial_ms ? 2 : 1;
-        } else {
-            (void)cudaGetLastError();
-            M.hot_choice = 1;
-        }
-    }
     dev_free(brec); dev_free(xhot); dev_free(xhotp);
     CUDA_TRY(err, e);
     return GrB_SUCCESS;
@@ -582,15 +554,16 @@ static GrB_Info seg_run_typed(const SR &sr, CsrArrays &M, int64_t mrows, int64_t
 
 GrB_Info spmv_seg_run(int type_code, int add_op, int mul_op, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz,
                       const void *avals, const void *x, const uint8_t *xp, void *t_vals, uint8_t *t_present,
-                      const void *epi_typed, std::string *err, bool *handled) {
+                      const void *epi_typed, std::string *err, bool *handled, int hot_mode, bool *used_hot) {
     *handled = false;
+    if (used_hot) *used_hot = false;
     // 128-bit loads: the index and value arrays must be 16-byte aligned (library allocations always are)
     if (((uintptr_t)M.idx & 15) || ((uintptr_t)avals & 15)) return GrB_SUCCESS;
     GrB_Info info = GrB_SUCCESS;
     GRB_DISPATCH_TYPE(type_code, T, {
         GRB_DISPATCH_SEMIRING(add_op, mul_op, T, SRT, sr, {
             info = seg_run_typed<SRT, T>(sr, M, mrows, ncols, nnz, (const T *)avals, (const T *)x, xp, (T *)t_vals, t_present,
-                                         *reinterpret_cast<const VecEpi<T> *>(epi_typed), err, handled);
+                                         *reinterpret_cast<const VecEpi<T> *>(epi_typed), err, handled, hot_mode, used_hot);
         });
     });
     return info;

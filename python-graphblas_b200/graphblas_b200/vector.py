@@ -224,8 +224,53 @@ class Vector(BaseType):
             expr.new(name="")  # incompatible shape; raise now
         return expr
 
+    def _as_matrix(self, *, name=None):
+        """This vector as an n x 1 Matrix (reference core/vector.py:193-209).  The reference's vanilla backend fills a fresh
+        Matrix with a column assign; here the column is built on the device by one scan + one compaction kernel."""
+        from .matrix import Matrix
+
+        h = ctypes.c_void_p()
+        out = Matrix._from_handle(h, self.dtype, self._size, 1, name or f"(GrB_Matrix){self.name}")
+        call("GrB_cuda_Matrix_from_Vector", [ctypes.byref(h), self])
+        return out
+
     def inner(self, other, op=None):
-        raise NotImplementedError("Vector.inner (vector cast to matrix) is outside this backend's hot path")
+        """reference core/vector.py:1715-1744: s = v' (+).(x) w, run as GrB_vxm against w cast to an n x 1 matrix; the result is
+        a Scalar (empty when no index is shared)."""
+        if type(other) is not Vector:
+            raise TypeError(f"inner expects a Vector, got {type(other).__name__}")
+        op = operator.semiring.plus_times if op is None else op
+        op = operator.get_typed_op(op, self.dtype, other.dtype, kind="semiring")
+        if op.opclass != "Semiring":
+            raise TypeError(f"inner expects a Semiring, got {op.opclass}")
+        if self._size != other._size:
+            raise DimensionMismatch(f"inner: sizes differ ({self._size} vs {other._size})")
+        me = self
+
+        def thunk():
+            w = Vector(op.return_type, 1)
+            w << VectorExpression("inner", "GrB_vxm", [me, other._as_matrix()], op=op, size=1)
+            return w[0].new().value
+
+        return ScalarExpression(op.return_type, thunk)
+
+    def outer(self, other, op=None):
+        """reference core/vector.py:1746-1787: C = v (any).(op) w', run as GrB_mxm of the two column matrices with GrB_DESC_T1."""
+        from .matrix import MatrixExpression
+
+        if type(other) is not Vector:
+            raise TypeError(f"outer expects a Vector, got {type(other).__name__}")
+        op = operator.binary.times if op is None else op
+        op = operator.get_typed_op(op, self.dtype, other.dtype, kind="binary")
+        if op.opclass == "Monoid":
+            op = op.binaryop
+        if op.opclass != "BinaryOp":
+            raise TypeError(f"outer expects a BinaryOp or Monoid, got {op.opclass}")
+        sr = getattr(operator.semiring, f"any_{op.parent.name}", None)
+        if sr is None or op.type not in sr:
+            raise NotImplementedError(f"no builtin semiring any_{op.parent.name}[{op.type.name}] behind Vector.outer")
+        return MatrixExpression("outer", "GrB_mxm", [self._as_matrix(), other._as_matrix()], op=sr[op.type],
+                                nrows=self._size, ncols=other._size, bt=True)
 
     def ewise_add(self, other, op=None):
         op = operator.monoid.plus if op is None else op

@@ -48,8 +48,8 @@ def test_mxv_degree_identities(gb, torch):
     A = gb.cuda.matrix_from_device_csr(ip, c, ones, n, n)
     x = gb.cuda.vector_from_torch(torch.ones(n, dtype=torch.float32, device=c.device))
     results = {}
-    for method in ("merge", "hot", "rowwarp"):
-        gb.cuda.set_option("spmv", "merge" if method == "hot" else method)
+    for method in ("merge", "seg", "hot", "rowwarp"):
+        gb.cuda.set_option("spmv", "seg" if method == "hot" else method)
         gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")   # hot-column cache of the pull kernel forced / off
         y = A.mxv(x, gb.semiring.plus_times).new()
         vals, pres = _vec_to_torch(gb, torch, y)
@@ -69,8 +69,8 @@ def test_mxv_degree_identities(gb, torch):
     x0 = gb.cuda.vector_from_torch(torch.zeros(n, dtype=torch.int64, device=c.device))
     rows = torch.repeat_interleave(torch.arange(n, device=c.device), deg)
     want = torch.full((n,), 1 << 62, dtype=torch.int64, device=c.device).scatter_reduce(0, rows, w, "amin")
-    for method in ("merge", "hot", "rowwarp"):
-        gb.cuda.set_option("spmv", "merge" if method == "hot" else method)
+    for method in ("merge", "seg", "hot", "rowwarp"):
+        gb.cuda.set_option("spmv", "seg" if method == "hot" else method)
         gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")
         y = W.mxv(x0, gb.semiring.min_plus).new()
         vals, pres = _vec_to_torch(gb, torch, y)
@@ -90,6 +90,15 @@ def test_mxv_degree_identities(gb, torch):
             outs.append(_vec_to_torch(gb, torch, Ad.mxv(xv, gb.semiring.plus_times).new()))
         gb.cuda.set_option("spmv_hot", "auto")
         assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    # "auto": the first multiplies with a CSR are the library's timed trial (merge / segmented / segmented + hot columns,
+    # two runs each), then the winner is kept -- every one of them must return the same exact result
+    for M, xv, sr in ((Ad, gb.cuda.vector_from_torch(xr, pr), gb.semiring.plus_times), (W, x0, gb.semiring.min_plus)):
+        gb.cuda.set_option("spmv", "merge")
+        ref_v, ref_p = (t.clone() for t in _vec_to_torch(gb, torch, M.mxv(xv, sr).new()))
+        gb.cuda.set_option("spmv", "auto")
+        for it in range(9):
+            got_v, got_p = _vec_to_torch(gb, torch, M.mxv(xv, sr).new())
+            assert torch.equal(got_p, ref_p) and torch.equal(got_v[ref_p.bool()], ref_v[ref_p.bool()]), it
     # pull over the cached transpose == push: vxm(x, A) column sums == in-degree
     indeg = torch.bincount(c.long(), minlength=n)
     for vm in ("pull", "push"):

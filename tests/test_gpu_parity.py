@@ -207,7 +207,7 @@ def test_vector_multiplies_vs_oracle(gb, semiring, dtype):
             for (use_mask, comp, struct, repl, accum) in [(False, False, False, False, None), (True, False, True, False, None),
                                                           (True, True, True, True, None), (True, False, False, True, accum_name),
                                                           (True, True, False, False, accum_name), (False, False, False, False, accum_name)]:
-                for method, vxm_method, hot in [("merge", "pull", "0"), ("merge", "pull", "1"), ("merge", "pull", "cap"),
+                for method, vxm_method, hot in [("merge", "pull", "0"), ("seg", "pull", "0"), ("seg", "pull", "1"), ("seg", "pull", "cap"),
                                                 ("rowwarp", "push", "auto"), ("auto", "auto", "auto")]:
                     gb.cuda.set_option("spmv", method)
                     gb.cuda.set_option("vxm_method", vxm_method)
@@ -344,7 +344,7 @@ def test_rmat_parity(gb, scale):
     v = gb.Vector.from_coo(np.arange(n), x, size=n)
     vb = R.BigVec(x, np.ones(n, np.uint8))
     for method in ("merge", "hot", "hotcap", "rowwarp"):
-        gb.cuda.set_option("spmv", "merge" if method.startswith("hot") else method)
+        gb.cuda.set_option("spmv", "seg" if method.startswith("hot") else method)
         gb.cuda.set_option("spmv_hot", "1" if method.startswith("hot") else "0")
         gb.cuda.set_option("spmv_hot_cap", "300" if method == "hotcap" else "0")
         for sr in ("min_plus", "plus_times", "plus_second", "any_pair"):
@@ -493,3 +493,38 @@ def test_io_roundtrips(gb):
     assert big.nvals == 0
     with pytest.raises((gb.exceptions.OutOfMemory, gb.exceptions.IndexOutOfBound)):
         big.build([0, 2**59], [0, 1])
+
+
+def test_inner_outer(gb):
+    """Vector.inner / Vector.outer run through GrB_vxm / GrB_mxm on the vector as an n x 1 matrix.
+    Known answers from reference tests/test_vector.py:1496-1547, then seeded vectors against the oracle (exact)."""
+    v = gb.Vector.from_coo([1, 3, 4, 6], [1, 1, 2, 0], size=7)
+    assert v.inner(v).new().value == 6 and (v @ v).new().value == 6
+    assert v.inner(v, gb.semiring.min_plus).new().value == 0
+    w = gb.Vector.from_coo([0, 2], [5, 7], size=7)
+    assert v.inner(w).new().value is None and v.inner(w).new().is_empty
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        v.inner(gb.Vector.from_coo([0], [1], size=8))
+    C = gb.Matrix.from_coo([1, 3, 4, 6], [0, 0, 0, 0], [1, 1, 2, 0], nrows=7, ncols=1)
+    Rm = gb.Matrix.from_coo([0, 0, 0, 0], [1, 3, 4, 6], [1, 1, 2, 0], nrows=1, ncols=7)
+    expected = C.mxm(Rm).new()
+    assert v.outer(v).new().isequal(expected) and v.outer(v, gb.monoid.times).new().isequal(expected)
+    assert v._as_matrix().isequal(C)
+    rng = np.random.default_rng(5)
+    for dtype, sr, bop in [(np.int64, "plus_times", "times"), (np.float64, "min_plus", "plus"), (np.int32, "max_plus", "min"),
+                           (np.float32, "plus_times", "first")]:
+        for n, m in [(1, 1), (50, 50), (3000, 777)]:
+            iu = np.unique(rng.integers(0, n, size=max(1, n // 2)))
+            iv = np.unique(rng.integers(0, n, size=max(1, n // 3)))
+            iw = np.unique(rng.integers(0, m, size=max(1, m // 3)))
+            xu, xv, xw = (H.random_values(rng, k.size, dtype) for k in (iu, iv, iw))
+            gu, gv, gw = gb.Vector.from_coo(iu, xu, size=n), gb.Vector.from_coo(iv, xv, size=n), gb.Vector.from_coo(iw, xw, size=m)
+            ou, ov, ow = (S.SpVec.from_coo(i, x, size=sz, dtype=dtype) for i, x, sz in ((iu, xu, n), (iv, xv, n), (iw, xw, m)))
+            want, _ = S.inner(sr, ou, ov)
+            got = gu.inner(gv, getattr(gb.semiring, sr)).new().value
+            assert (got is None and want is None) or got == want, (dtype, sr, n, got, want)
+            if n * m <= 60000:
+                wo = S.outer(bop, ou, ow)
+                I, J, X = gu.outer(gw, getattr(gb.binary, bop)).new().to_coo()
+                oi, oj, ox = wo.to_coo()
+                assert np.array_equal(I.astype(np.int64), oi) and np.array_equal(J.astype(np.int64), oj) and np.array_equal(X, ox.astype(X.dtype))

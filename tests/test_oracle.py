@@ -216,3 +216,18 @@ def test_int64_wraps_like_reference_test_power():
         Pb = R.mxm_T("plus_times", Pb, Ab)
     assert all(np.array_equal(p, q) for p, q in zip(P.to_coo(), Pb.to_coo()))
     assert np.abs(P.to_coo()[2]).max() > 2**40  # did exercise large magnitudes
+
+
+def test_inner_outer_reference_known_answers():
+    """reference tests/test_vector.py:1496-1547: v.inner(v) == 6 for the fixture v (indices [1,3,4,6], values [1,1,2,0]);
+    v.outer(v) equals the product of the column and row forms."""
+    v = S.SpVec.from_coo([1, 3, 4, 6], [1, 1, 2, 0], size=7, dtype=np.int64)
+    val, dt = S.inner("plus_times", v, v)
+    assert int(val) == 6 and dt == np.int64
+    w = S.SpVec.from_coo([0, 2], [5, 7], size=7, dtype=np.int64)
+    assert S.inner("plus_times", v, w)[0] is None                 # no shared index -> empty scalar
+    assert int(S.inner("min_plus", v, v)[0]) == 0                 # min(1+1, 1+1, 2+2, 0+0)
+    out = S.outer("times", v, v)
+    want = S.SpMat(7, 7, np.int64)
+    S.mxm(want, None, None, "plus_times", v.as_col(), v.as_row())
+    assert out.e == want.e and len(out.e) == 16 and int(out.e[(4, 4)]) == 4 and int(out.e[(6, 1)]) == 0
