@@ -737,6 +737,240 @@ __global__ void spgemm_block_elect_kernel(SR sr, const int32_t *__restrict__ row
     }
 }
 
+// ------------------------------------------------------------------ grouped small rows (numeric, one-pass, unmasked)
+// A row of a sparse product has only a few hundred products, so a CTA per row spends most of its instructions on fixed
+// per-row work (table init, staging, drain, barriers) and most of its time waiting on the dependent load chain of that one
+// row.  Here a 256-thread CTA takes a GROUP of consecutive rows -- all rows with <= R products whose staging offsets fall in
+// one window of the flops prefix, < G products in total -- gives every row its own slice of one shared-memory table, and
+// walks the products of the WHOLE group as one flat index space: every thread always has work, the A entries of the group
+// are one contiguous, coalesced read, and the owner-election rounds (see above) are full.  Rows with more than R products
+// keep the CTA-per-row kernels.
+constexpr int GROUP_THREADS = 256;
+constexpr int GROUP_RMAX = 256;   // rows per batch == threads, so the per-row scan is one pass
+__host__ __device__ __forceinline__ int group_tsize(int64_t c, int tf8) { return (int)((c * tf8) >> 3) + 2; }
+
+struct SmallRowPred {
+    const int64_t *flops; int64_t R;
+    __device__ __forceinline__ bool operator()(const int &i) const { const int64_t f = flops[i]; return f > 0 && f <= R; }
+};
+// big[i] = flops of the rows the bins keep (the others are binned as empty); sf[q] = flops of the q-th small row
+__global__ void split_flops_kernel(int64_t nrows, const int64_t *__restrict__ flops, int64_t R, int64_t *__restrict__ big) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= nrows; i += s) {
+        const int64_t f = i < nrows ? flops[i] : 0;
+        big[i] = f <= R ? 0 : f;
+    }
+}
+__global__ void gather_small_flops_kernel(int64_t n_small, const int32_t *__restrict__ small_rows, const int64_t *__restrict__ flops,
+                                          int64_t *__restrict__ sf) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; q <= n_small; q += s) sf[q] = q < n_small ? flops[small_rows[q]] : 0;
+}
+// g_start[k] = first position of the small-row list whose flops prefix is >= k * window; g_start[n_groups] = n_small
+__global__ void group_starts_kernel(int64_t n_small, const int64_t *__restrict__ F, int64_t window, int64_t n_groups,
+                                    int64_t *__restrict__ g_start) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_groups) return;
+    if (k == n_groups) { g_start[k] = n_small; return; }
+    const int64_t target = k * window;
+    int64_t lo = 0, hi = n_small;   // first q in [0, n_small] with F[q] >= target
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (F[mid] >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    g_start[k] = lo;
+}
+
+static inline size_t group_smem_bytes(int tslots, size_t val_bytes) {
+    size_t b = (((size_t)tslots * (val_bytes + 4)) + 15) & ~(size_t)15;                       // vals | keys
+    b += (size_t)GROUP_THREADS * 8;                                                          // s_bs
+    b += (size_t)(GROUP_THREADS + 4) * 4;                                                    // s_off
+    b += (size_t)GROUP_THREADS * 4 * 2;                                                      // s_tb, s_ts
+    b += (size_t)(GROUP_RMAX + 4) * 4 * 2;                                                   // s_tbase, s_aoff
+    b += (size_t)GROUP_RMAX * 8;                                                             // s_abeg
+    b += (((size_t)GROUP_THREADS * val_bytes) + 15) & ~(size_t)15;                           // s_av
+    return b;
+}
+
+template <typename SR, typename T>
+__global__ void __launch_bounds__(GROUP_THREADS)
+spgemm_group_elect_kernel(SR sr, const int64_t *__restrict__ g_start, const int32_t *__restrict__ small_rows, int tf8, int tslots,
+                          const int64_t *__restrict__ flops, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj,
+                          const T *__restrict__ Ax, const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj,
+                          const T *__restrict__ Bx, int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op,
+                          int32_t *__restrict__ Oj, T *__restrict__ Ox) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_wsum[GROUP_THREADS / 32], s_wsum2[GROUP_THREADS / 32];
+    constexpr int NT = GROUP_THREADS;
+    const int tid = threadIdx.x, wlane = tid & 31, warp = tid >> 5;
+    T *vals = reinterpret_cast<T *>(s_raw);
+    int *keys = reinterpret_cast<int *>(vals + tslots);
+    unsigned char *q = s_raw + ((((size_t)tslots * (sizeof(T) + 4)) + 15) & ~(size_t)15);
+    int64_t *s_bs = reinterpret_cast<int64_t *>(q); q += (size_t)NT * 8;
+    int *s_off = reinterpret_cast<int *>(q); q += (size_t)(NT + 4) * 4;
+    int *s_tb = reinterpret_cast<int *>(q); q += (size_t)NT * 4;
+    int *s_ts = reinterpret_cast<int *>(q); q += (size_t)NT * 4;
+    int *s_tbase = reinterpret_cast<int *>(q); q += (size_t)(GROUP_RMAX + 4) * 4;
+    int *s_aoff = reinterpret_cast<int *>(q); q += (size_t)(GROUP_RMAX + 4) * 4;
+    int64_t *s_abeg = reinterpret_cast<int64_t *>(q); q += (size_t)GROUP_RMAX * 8;
+    T *s_av = reinterpret_cast<T *>(q);
+
+    const int64_t gr0 = g_start[blockIdx.x], gr1 = g_start[blockIdx.x + 1];
+    for (int64_t rb = gr0; rb < gr1; rb += GROUP_RMAX) {
+        const int nr = (int)((gr1 - rb < GROUP_RMAX) ? (gr1 - rb) : GROUP_RMAX);
+        __syncthreads();   // the previous batch's drain is done with the table and the row arrays
+        // ---- per-row slices of the table and the (batch-local) prefix of the rows' A-entry counts; rb indexes the small-row list
+        int ts = 0, deg = 0;
+        if (tid < nr) {
+            const int64_t row = small_rows[rb + tid];
+            ts = group_tsize(flops[row], tf8);
+            const int64_t ab = Ap[row];
+            deg = (int)(Ap[row + 1] - ab);
+            s_abeg[tid] = ab;
+        }
+        int incl = ts, dincl = deg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o), dup = __shfl_up_sync(0xffffffffu, dincl, o);
+            if (wlane >= o) { incl += up; dincl += dup; }
+        }
+        if (wlane == 31) { s_wsum[warp] = incl; s_wsum2[warp] = dincl; }
+        __syncthreads();
+        int wbase = 0, dbase = 0;
+        for (int w = 0; w < warp; w++) { wbase += s_wsum[w]; dbase += s_wsum2[w]; }
+        if (tid < nr) { s_tbase[tid] = wbase + incl - ts; s_aoff[tid] = dbase + dincl - deg; }
+        if (tid == nr - 1) { s_tbase[nr] = wbase + incl; s_aoff[nr] = dbase + dincl; }
+        __syncthreads();
+        const int total_slots = s_tbase[nr];   // <= tslots by construction of the groups
+        for (int t = tid; t < total_slots; t += NT) keys[t] = HASH_EMPTY;
+        const int a_total = s_aoff[nr];
+        // ---- the A entries of the batch, a chunk of NT at a time
+        for (int c0 = 0; c0 < a_total; c0 += NT) {
+            const int chunk_n = (a_total - c0 < NT) ? (a_total - c0) : NT;
+            int len = 0;
+            if (tid < chunk_n) {
+                const int k = c0 + tid;
+                int lo = 0, hi = nr - 1;   // owning row: the last r with s_aoff[r] <= k (rows without entries are skipped)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_aoff[mid] <= k) lo = mid;
+                    else hi = mid - 1;
+                }
+                const int tb = s_tbase[lo];
+                s_tb[tid] = tb;
+                s_ts[tid] = s_tbase[lo + 1] - tb;
+                const int64_t ak = s_abeg[lo] + (k - s_aoff[lo]);
+                const int32_t br = Aj[ak];
+                const int64_t bs = Bp[br];
+                len = (int)(Bp[br + 1] - bs);
+                s_bs[tid] = bs;
+                if (sr.reads_a()) s_av[tid] = Ax[ak];
+            }
+            int pin = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, pin, o);
+                if (wlane >= o) pin += up;
+            }
+            __syncthreads();   // s_wsum free again; also orders the key init / the previous chunk's rounds before this chunk's
+            if (wlane == 31) s_wsum[warp] = pin;
+            __syncthreads();
+            int pbase = 0;
+            for (int w = 0; w < warp; w++) pbase += s_wsum[w];
+            s_off[tid] = pbase + pin - len;
+            if (tid == NT - 1) s_off[NT] = pbase + pin;
+            __syncthreads();
+            const int P = s_off[NT];
+            for (int base0 = 0; base0 < P; base0 += NT * UNROLL) {   // uniform trip counts: barriers inside
+                int jj[UNROLL], hb[UNROLL], hs[UNROLL];
+                T bb[UNROLL], aa[UNROLL];
+                int pp = base0 + warp * (32 * UNROLL) + wlane;
+                int lo = 0;
+                if (pp < P) {
+                    int hi = chunk_n - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_off[mid] <= pp) lo = mid;
+                        else hi = mid - 1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    jj[u] = HASH_EMPTY;
+                    if (pp < P) {
+                        while (s_off[lo + 1] <= pp) lo++;
+                        const int64_t e = s_bs[lo] + (pp - s_off[lo]);
+                        jj[u] = Bj[e];
+                        if (sr.reads_b()) bb[u] = Bx[e];
+                        if (sr.reads_a()) aa[u] = s_av[lo];
+                        hb[u] = s_tb[lo];
+                        hs[u] = s_ts[lo];
+                    }
+                    pp += 32;
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    if (base0 + u * 32 >= P) break;   // uniform: no thread of the CTA has a product in this slot
+                    const int j = jj[u];
+                    bool have = j != HASH_EMPTY;
+                    const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                    const int tb = have ? hb[u] : 0, te = have ? hb[u] + hs[u] : 1;
+                    int h = have ? tb + (int)hash_slot(j, (unsigned)hs[u]) : 0;
+                    while (true) {
+                        bool claim = false;
+                        if (have) {
+                            int k = keys[h];
+                            while (k != HASH_EMPTY && k != j) {
+                                h = (h + 1 == te) ? tb : h + 1;
+                                k = keys[h];
+                            }
+                            if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                            else claim = true;
+                        }
+                        if (!__syncthreads_or(claim)) break;   // barrier: every probe of this round has read its keys
+                        if (claim) elect_store(&keys[h], -(tid + 2));
+                        __syncthreads();
+                        if (claim && elect_load(&keys[h]) == -(tid + 2)) {
+                            vals[h] = pr;
+                            elect_store(&keys[h], j);
+                            have = false;
+                            claim = false;
+                        }
+                        __syncthreads();
+                        if (claim) {
+                            if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
+                            else h = (h + 1 == te) ? tb : h + 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- drain: a warp per row, ballot compaction into the staging row
+        for (int r = warp; r < nr; r += NT / 32) {
+            const int tb = s_tbase[r], tsz = s_tbase[r + 1] - tb;
+            const int64_t row = small_rows[rb + r];
+            const int64_t ob = Op[row];
+            int outpos = 0;
+            for (int t0 = 0; t0 < tsz; t0 += 32) {
+                const int t = t0 + wlane;
+                const int key = t < tsz ? keys[tb + t] : HASH_EMPTY;
+                const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+                if (key >= 0) {
+                    const int pos = outpos + __popc(m & ((1u << wlane) - 1u));
+                    Oj[ob + pos] = key;
+                    Ox[ob + pos] = vals[tb + t];
+                }
+                outpos += __popc(m);
+            }
+            if (wlane == 0) row_nnz[row] = outpos;
+        }
+    }
+}
+
 __global__ void gtable_sizes_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt,
                                     int64_t *__restrict__ sizes) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -848,6 +1082,10 @@ static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const i
     return GrB_SUCCESS;
 }
 
+struct GroupArgs {   // grouped small rows (spgemm_group_elect_kernel); n_groups == 0: not used
+    const int64_t *g_start = nullptr; const int32_t *small_rows = nullptr; int64_t n_groups = 0; int64_t R = 0; int tf8 = 12; int tslots = 0;
+    const int64_t *flops = nullptr;
+};
 struct HashArgs {
     const int64_t *Ap; const int32_t *Aj; const void *Ax;
     const int64_t *Bp; const int32_t *Bj; const void *Bx;
@@ -961,7 +1199,8 @@ template <typename T> static size_t numeric_entry_bytes() { return (Packed<T>::v
 // numeric pass writing row i at O*[Op[i]...]; row_nnz (optional) receives exact counts
 template <typename T>
 static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p, const Bins &bins, const int64_t *cnt,
-                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, MaskArgs mk, std::string *err) {
+                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, MaskArgs mk, std::string *err,
+                                     const GroupArgs &ga = GroupArgs()) {
     GrB_Info info = GrB_SUCCESS;
     const int T_code = type_code_of<T>();
     GRB_DISPATCH_SEMIRING(op->add, op->mul, T, SRT, sr, {
@@ -971,8 +1210,23 @@ static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p,
         if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
         if (!info) {
             HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt, mk};
-            if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
-            else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
+            if constexpr (sizeof(T) >= 4) {
+                if (ga.n_groups > 0) {   // small rows first: many short CTAs, the big-row bins then fill the tail
+                    const size_t smem = group_smem_bytes(ga.tslots, sizeof(T));
+                    auto kern = spgemm_group_elect_kernel<SRT, T>;
+                    cudaError_t ge = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (ge == cudaSuccess) {
+                        LAUNCH_NOTE("spgemm_numeric_group");
+                        kern<<<(unsigned)ga.n_groups, GROUP_THREADS, smem, g_stream>>>(sr, ga.g_start, ga.small_rows, ga.tf8, ga.tslots, ga.flops, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+                        ge = cudaGetLastError();
+                    }
+                    if (ge != cudaSuccess) info = cuda_fail(err, ge, "grouped spgemm kernel");
+                }
+            }
+            if (!info) {
+                if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
+                else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
+            }
         }
         dev_free(atmp);
         dev_free(btmp);
@@ -1013,6 +1267,8 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     int64_t *Sp = nullptr;
     int32_t *Sj = nullptr;
     void *Sx = nullptr;
+    int64_t *gsmall = nullptr, *gbig = nullptr, *ggroups = nullptr;   // grouped small rows (one-pass numeric)
+    int32_t *gsrows = nullptr;
     unsigned long long *red = dev_alloc_t<unsigned long long>(2);
     Bins fbins, nbins;
     GrB_Matrix Tm = nullptr;
@@ -1127,7 +1383,66 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         size_t entry = 12;
         GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
         phase_mark("mxm_plan");
-        info = make_bins(&fbins, entry, p.m, flops, err);
+        // rows with <= R products go to the grouped kernel (needs a >= 4-byte domain for its tables); the bins see the rest
+        GroupArgs ga;
+        const int64_t *bin_cnt = flops;
+        if (es >= 4 && opt_get_int("spgemm_group", 0) != 0) {   // experimental, off by default: measured slower
+            const int64_t G = std::max<long>(512, opt_get_int("spgemm_group_g", 3072));
+            const int64_t R = std::min<int64_t>(G / 2, std::max<long>(1, opt_get_int("spgemm_group_r", 1024)));
+            ga.tf8 = (int)std::max<long>(9, opt_get_int("spgemm_group_tf8", 12));
+            ga.R = R;
+            ga.tslots = (int)((G * ga.tf8) >> 3) + 2 * GROUP_RMAX + 8;
+            ga.flops = flops;
+            gbig = dev_alloc_t<int64_t>((size_t)p.m + 1);
+            gsrows = dev_alloc_t<int32_t>((size_t)p.m + 1);
+            int *d_count = dev_alloc_t<int>(1);
+            void *tmp = nullptr;
+            if (!gbig || !gsrows || !d_count) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group arrays");
+            if (!info && group_smem_bytes(ga.tslots, es) > (size_t)226 * 1024) info = set_error(err, GrB_INVALID_VALUE, "spgemm_group_g too large for shared memory");
+            int n_small = 0;
+            if (!info) {
+                note_launch("split_flops");
+                split_flops_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, R, gbig);
+                size_t tb = 0;
+                cub::CountingInputIterator<int> it(0);
+                cub::DeviceSelect::If(nullptr, tb, it, gsrows, d_count, (int)p.m, SmallRowPred{flops, R}, g_stream);
+                tmp = dev_alloc(tb);
+                if (!tmp) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group scratch");
+                if (!info) {
+                    note_launch("small_rows");
+                    cudaError_t e = cub::DeviceSelect::If(tmp, tb, it, gsrows, d_count, (int)p.m, SmallRowPred{flops, R}, g_stream);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_small, d_count, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+                    if (e != cudaSuccess) info = cuda_fail(err, e, "small-row list");
+                }
+            }
+            int64_t total_small = 0;
+            if (!info && n_small > 0) {
+                gsmall = dev_alloc_t<int64_t>((size_t)n_small + 1);
+                if (!gsmall) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group prefix");
+                if (!info) {
+                    note_launch("gather_small_flops");
+                    gather_small_flops_kernel<<<copy_blocks, 256, 0, g_stream>>>(n_small, gsrows, flops, gsmall);
+                    info = exclusive_scan_i64(gsmall, (int64_t)n_small + 1, err);
+                }
+                if (!info) total_small = read_i64(gsmall + n_small);
+            }
+            if (!info && total_small > 0) {
+                const int64_t window = G - R;
+                ga.n_groups = (total_small + window - 1) / window;
+                ggroups = dev_alloc_t<int64_t>((size_t)ga.n_groups + 1);
+                if (!ggroups) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group starts");
+                if (!info) {
+                    note_launch("group_starts");
+                    group_starts_kernel<<<(unsigned)((ga.n_groups + 1 + 255) / 256), 256, 0, g_stream>>>(n_small, gsmall, window, ga.n_groups, ggroups);
+                    ga.g_start = ggroups;
+                    ga.small_rows = gsrows;
+                }
+            }
+            dev_free(d_count); dev_free(tmp);
+            bin_cnt = gbig;
+        }
+        if (!info) info = make_bins(&fbins, entry, p.m, bin_cnt, err);
         phase_mark("mxm_bins");
         if (!info) {
             Sp = dev_alloc_t<int64_t>((size_t)p.m + 1);
@@ -1143,7 +1458,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         if (!info) {
             GrB_Info i3 = GrB_NOT_IMPLEMENTED;
             phase_mark("mxm_staging_alloc");
-            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, flops, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err));
+            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, bin_cnt, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err, ga));
             info = i3;
             phase_mark("mxm_numeric_launch");
         }
@@ -1211,6 +1526,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     phase_mark("mxm_compact_launch");
     dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(fbins.rows); dev_free(nbins.rows);
     dev_free(Sp); ws_release(0, Sj); ws_release(1, Sx);
+    dev_free(gsmall); dev_free(gbig); dev_free(ggroups); dev_free(gsrows);
     if (info || symbolic_only) {
         if (Tm) GrB_Matrix_free(&Tm);
         return info;

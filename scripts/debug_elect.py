@@ -19,8 +19,8 @@ for scale in [int(a) for a in sys.argv[1:]] or [16, 20]:
     for srname in ("plus_times", "any_pair"):
         sr = getattr(gb.semiring, srname)
         res = {}
-        for elect in ("0", "1"):
-            gb.cuda.set_option("spgemm_elect", elect)
+        for elect in ("0", "1"):  # group kernel off / on
+            gb.cuda.set_option("spgemm_group", elect)
             C = A.mxm(A, sr).new()
             gb.cuda.matrix_sort(C)
             p_, j_, x_ = gb.cuda.matrix_as_torch(C) if hasattr(gb.cuda, "matrix_as_torch") else (None, None, None)
@@ -43,4 +43,4 @@ for scale in [int(a) for a in sys.argv[1:]] or [16, 20]:
                 print("  cols a", a[1][s:e][db].tolist(), "b", b[1][s:e][db].tolist(), "vals a", a[2][s:e][db].tolist(), "b", b[2][s:e][db].tolist())
                 badrows = torch.unique(torch.searchsorted(a[0], bad, right=True) - 1)
                 print("  bad rows", badrows.numel(), "flops of bad rows: min", int(flops[badrows].min()), "max", int(flops[badrows].max()), "sample", flops[badrows][:12].tolist())
-    gb.cuda.set_option("spgemm_elect", None)
+    gb.cuda.set_option("spgemm_group", None)

@@ -16,11 +16,12 @@ A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
 sr = gb.semiring.plus_times
 SETS = [
     {},
-    {"spgemm_thr_7": "256", "spgemm_thr_8": "256"},
-    {"spgemm_thr_5": "64", "spgemm_thr_6": "64"},
-    {"spgemm_thr_6": "256", "spgemm_thr_9": "512", "spgemm_thr_10": "512"},
-    {"spgemm_elect": "1", "spgemm_elect_from_bin": "7"},
-    {},
+    {"spgemm_group": "0"},
+    {"spgemm_group_g": "2048", "spgemm_group_r": "768"},
+    {"spgemm_group_g": "4096", "spgemm_group_r": "1536"},
+    {"spgemm_group_g": "6144", "spgemm_group_r": "2048"},
+    {"spgemm_group_g": "3072", "spgemm_group_r": "1024", "spgemm_group_tf8": "16"},
+    {"spgemm_group_g": "8192", "spgemm_group_r": "3072", "spgemm_group_tf8": "10"},
 ]
 if len(sys.argv) > 2:
     SETS = [json.loads(a) for a in sys.argv[2:]]

@@ -528,3 +528,26 @@ def test_inner_outer(gb):
                 I, J, X = gu.outer(gw, getattr(gb.binary, bop)).new().to_coo()
                 oi, oj, ox = wo.to_coo()
                 assert np.array_equal(I.astype(np.int64), oi) and np.array_equal(J.astype(np.int64), oj) and np.array_equal(X, ox.astype(X.dtype))
+
+
+@pytest.mark.parametrize("opts", [{"spgemm_elect": "1"}, {"spgemm_group": "1"}, {"spgemm_group": "1", "spgemm_group_g": "512", "spgemm_group_r": "64"},
+                                  {"spgemm_cas_first": "0"}, {"spgemm_mode": "twopass"}],
+                         ids=["elect", "group", "group-small", "probe-first", "twopass"])
+def test_mxm_optional_kernels_match_default(gb, opts):
+    """The optional SpGEMM insert kernels (atomics-free owner election per row / per group of rows, probe-before-CAS, two-pass)
+    must produce exactly the default kernels' result: integer values bit-exact, same pattern, on an R-MAT product whose
+    rows span the warp, CTA and global-table bins."""
+    r, c, n = H.rmat_edges(13, a=0.45, b=0.15, c=0.15, seed=42)
+    rng = np.random.default_rng(3)
+    for dtype, sr in ((np.int32, "plus_times"), (np.int64, "min_plus"), (np.float64, "plus_times")):
+        vals = rng.integers(1, 4, r.size).astype(dtype)
+        A = gb.Matrix.from_coo(r, c, vals, nrows=n, ncols=n)
+        want = A.mxm(A, getattr(gb.semiring, sr)).new().to_coo()
+        for k, v in opts.items():
+            gb.cuda.set_option(k, v)
+        try:
+            got = A.mxm(A, getattr(gb.semiring, sr)).new().to_coo()
+        finally:
+            for k in opts:
+                gb.cuda.set_option(k, None)
+        assert all(np.array_equal(x, y) for x, y in zip(want, got)), (opts, dtype, sr)
