@@ -93,6 +93,8 @@ extern int g_num_sms;
 void note_launch(const char *name);
 struct KernelTimer { KernelTimer(const char *name); ~KernelTimer(); const char *name; cudaEvent_t a, b; bool on; };
 #define LAUNCH_NOTE(name) note_launch(name); KernelTimer _kt(name)
+cudaStream_t aux_stream(int i);      // two helper streams for concurrent kernels inside one call (nullptr when unavailable)
+bool profiling();                    // per-kernel timing mode: everything stays on g_stream
 void phase_mark(const char *name);   // option trace_host=1: host wall time since the previous mark goes to kernel-time slot "host:<name>" (nullptr: restart)
 
 GrB_Info set_error(std::string *slot, GrB_Info info, const char *fmt, ...);

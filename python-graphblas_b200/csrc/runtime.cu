@@ -72,6 +72,17 @@ KernelTimer::~KernelTimer() {
     }
 }
 
+cudaStream_t aux_stream(int i) {
+    static cudaStream_t aux[2] = {nullptr, nullptr};
+    if (i < 0 || i > 1) return nullptr;
+    if (!aux[i] && cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking) != cudaSuccess) {
+        (void)cudaGetLastError();
+        aux[i] = nullptr;
+    }
+    return aux[i];
+}
+bool profiling() { return g_profile; }
+
 void phase_mark(const char *name) {
     static std::chrono::steady_clock::time_point last;
     if (opt_get_int("trace_host", 0) == 0) return;

@@ -1100,9 +1100,31 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
     const size_t entry = Table::entry_bytes();
     const char *phase = NUMERIC ? "numeric" : "symbolic";
-    for (int b = 1; b < NBINS; b++) {
+    // The bins are independent (disjoint rows).  Big-table bins run one or two latency-bound CTAs per SM, small-row bins many
+    // short ones: on two helper streams they share the SMs instead of queueing behind each other, and the global-table bin
+    // (host-synchronising batches, launched last) runs on the library stream beside both.  Per-kernel profiling
+    // keeps everything on the library stream.
+    cudaStream_t aux0 = nullptr, aux1 = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool multi = !profiling() && opt_get_int("spgemm_streams", 0) != 0;
+    if (multi) {
+        aux0 = aux_stream(0);
+        aux1 = aux_stream(1);
+        if (!ev_fork) cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int q = 0; q < 2; q++)
+            if (!ev_join[q]) cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming);
+        multi = aux0 && aux1 && ev_fork && ev_join[0] && ev_join[1];
+        (void)cudaGetLastError();
+    }
+    if (multi) {
+        cudaEventRecord(ev_fork, g_stream);
+        cudaStreamWaitEvent(aux0, ev_fork, 0);
+        cudaStreamWaitEvent(aux1, ev_fork, 0);
+    }
+    const int big_from = (int)opt_get_int("spgemm_stream_split_bin", 8);
+    auto process = [&](int b, cudaStream_t st) -> GrB_Info {
         const int64_t n = (int64_t)bins.count[b];
-        if (n == 0) continue;
+        if (n == 0) return GrB_SUCCESS;
         const int32_t *rows = bins.rows + bins.start[b];
         const int cap = bins.spec.cap[b], threads = bins.spec.threads[b];
         if constexpr (NUMERIC && sizeof(T) >= 4) {
@@ -1116,18 +1138,18 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                     auto kern = spgemm_warp_elect_kernel<SR, T>;
                     if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     LAUNCH_NOTE("spgemm_numeric_warp");
-                    kern<<<(unsigned)((n + rpb - 1) / rpb), 32 * rpb, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+                    kern<<<(unsigned)((n + rpb - 1) / rpb), 32 * rpb, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
                 } else {
                     const size_t smem = block_elect_bytes(cap, threads, sizeof(T));
                     auto kern = spgemm_block_elect_kernel<SR, T>;
                     CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                     LAUNCH_NOTE("spgemm_numeric_block");
-                    kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+                    kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
                 }
                 cudaError_t le = cudaGetLastError();
                 if (le != cudaSuccess)
                     return set_error(err, GrB_PANIC, "spgemm elect kernel launch failed in bin %d (cap %d, %d threads, %lld rows): %s", b, cap, threads, (long long)n, cudaGetErrorString(le));
-                continue;
+                return GrB_SUCCESS;
             }
         }
         if (b <= 2) {
@@ -1137,13 +1159,13 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             auto kern = spgemm_warp_kernel<SR, T, NUMERIC, PACK>;
             if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
-            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, g_stream>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
+            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
         } else if (b < NBINS - 1) {
             const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
             CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
-            kern<<<(unsigned)n, threads, smem, g_stream>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
+            kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
@@ -1183,9 +1205,21 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
         if (le != cudaSuccess)
             return set_error(err, GrB_PANIC, "spgemm %s kernel launch failed in bin %d (cap %d, %d threads, %lld rows, entry %zu B): %s",
                              phase, b, cap, threads, (long long)n, entry, cudaGetErrorString(le));
+        return GrB_SUCCESS;
+    };
+    GrB_Info info = GrB_SUCCESS;
+    for (int b = NBINS - 2; b >= 1 && !info; b--) info = process(b, multi ? (b >= big_from ? aux0 : aux1) : g_stream);
+    if (!info) info = process(NBINS - 1, g_stream);   // global-table rows: library stream (its batches synchronise the host)
+    if (multi) {
+        cudaEventRecord(ev_join[0], aux0);
+        cudaEventRecord(ev_join[1], aux1);
+        cudaStreamWaitEvent(g_stream, ev_join[0], 0);
+        cudaStreamWaitEvent(g_stream, ev_join[1], 0);
     }
-    return GrB_SUCCESS;
+    return info;
 }
+
+
 
 struct SpgemmPlan {
     CsrArrays *A, *B;

@@ -16,12 +16,13 @@ A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
 sr = gb.semiring.plus_times
 SETS = [
     {},
-    {"spgemm_group": "0"},
-    {"spgemm_group_g": "2048", "spgemm_group_r": "768"},
-    {"spgemm_group_g": "4096", "spgemm_group_r": "1536"},
-    {"spgemm_group_g": "6144", "spgemm_group_r": "2048"},
-    {"spgemm_group_g": "3072", "spgemm_group_r": "1024", "spgemm_group_tf8": "16"},
-    {"spgemm_group_g": "8192", "spgemm_group_r": "3072", "spgemm_group_tf8": "10"},
+    {"spgemm_streams": "0"},
+    {"spgemm_stream_split_bin": "6"},
+    {"spgemm_stream_split_bin": "7"},
+    {"spgemm_stream_split_bin": "9"},
+    {"spgemm_stream_split_bin": "10"},
+    {},
+    {"spgemm_streams": "0"},
 ]
 if len(sys.argv) > 2:
     SETS = [json.loads(a) for a in sys.argv[2:]]
@@ -38,11 +39,11 @@ for opts in SETS:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    for _ in range(5):
         C = None
         C = A.mxm(A, sr).new()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = e0.elapsed_time(e1) / 5
     gb.cuda.set_option("profile", "1"); gb.cuda.kernel_times(reset=True)
     C = None
     C = A.mxm(A, sr).new()

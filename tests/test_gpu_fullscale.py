@@ -210,3 +210,25 @@ def test_masked_mxm_graph500_scale22(gb, torch):
     Fp, Fj, Fx = fast.to_csr()
     a, b = int(Cp[r0]), int(Cp[r1])
     assert np.array_equal(Cp[r0:r1 + 1] - Cp[r0], Fp) and np.array_equal(Cj[a:b], Fj) and np.array_equal(Cx[a:b], Fx)
+
+
+def test_lazy_sort_all_row_classes(gb, torch):
+    """The on-demand row sort (what finishes a 'jumbled' mxm result): rows of every size class -- warp (<= 32), shared-memory
+    bitonic (<= 512, <= 8192) and the batched segmented sort for longer rows -- against torch.sort, values carried along."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(21)
+    lens = torch.tensor([0, 1, 7, 32, 33, 500, 513, 4000, 8192, 8193, 20000, 70000, 3, 0, 100000], device=dev)
+    ncols = 1 << 20
+    ip = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev); ip[1:] = torch.cumsum(lens, 0)
+    cols = torch.cat([torch.randperm(ncols, device=dev, generator=g)[: int(l)] for l in lens]).to(torch.int32)
+    for dt in (torch.int8, torch.float32, torch.int64):
+        vals = torch.arange(cols.numel(), device=dev).to(dt)
+        A = gb.cuda.matrix_from_device_csr(ip, cols, vals, lens.numel(), ncols, sorted=False)
+        gb.cuda.matrix_sort(A)
+        p2, c2, v2 = gb.cuda.matrix_as_torch(A)
+        assert torch.equal(p2, ip)
+        for r in range(lens.numel()):
+            b, e = int(ip[r]), int(ip[r + 1])
+            want_c, order = torch.sort(cols[b:e].long())
+            assert torch.equal(c2[b:e].long(), want_c), (dt, r)
+            assert torch.equal(v2[b:e], vals[b:e][order]), (dt, r)
