@@ -213,6 +213,21 @@ GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void *Ax, GrB_In
                                       GrB_Matrix A, int sort);
 /* raw device views (valid until the object is next modified) */
 GrB_Info GrB_cuda_Matrix_device_csr(const GrB_Matrix A, int64_t **Ap, int32_t **Aj, void **Ax);
+/* matrix element-wise operations, all on the device: the C-API-2.0 names the reference calls
+   (graphblas/core/base.py:401-411 transpose; core/matrix.py:1972-2165 eWise; :2440-2533 apply) plus bind-1st/2nd and
+   reduce-to-scalar with the scalar passed by pointer + type (same convention as the GrB_cuda_Vector_* variants) */
+GrB_Info GrB_transpose(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Matrix A, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_apply(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_UnaryOp op, const GrB_Matrix A,
+                          const GrB_Descriptor desc);
+GrB_Info GrB_cuda_Matrix_apply_binop(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                     const GrB_Matrix A, const void *scalar, GrB_Type scalar_type, int scalar_first,
+                                     const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_eWiseAdd_BinaryOp(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                      const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_eWiseMult_BinaryOp(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                       const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc);
+GrB_Info GrB_cuda_Matrix_reduce(void *val, GrB_Type val_type, const GrB_BinaryOp accum, const GrB_Monoid op, const GrB_Matrix A,
+                                GrB_Index *nvals);
 /* v as an n x 1 matrix (column vector), built on the device: what Vector._as_matrix provides for Vector.inner / Vector.outer
    (reference graphblas/core/vector.py:193-209, 1715-1787) */
 GrB_Info GrB_cuda_Matrix_from_Vector(GrB_Matrix *A, const GrB_Vector v);

@@ -312,3 +312,68 @@ def outer(binop, u, v):
     column form).  Returns an SpMat."""
     T, D = _multiply(u.as_col(), v.as_row(), f"any_{binop}")
     return SpMat(u.size, v.size, D, T)
+
+
+# --------------------------------------------------------------------------- matrix element-wise operations (SURVEY 8f-1)
+COMPARE = {"eq": lambda x, y: x == y, "ne": lambda x, y: x != y, "lt": lambda x, y: x < y, "gt": lambda x, y: x > y,
+           "le": lambda x, y: x <= y, "ge": lambda x, y: x >= y}
+UNARY = {"identity": lambda x: x, "ainv": lambda x: -x, "abs": lambda x: abs(x), "one": lambda x: type(x)(1),
+         "lnot": lambda x: type(x)(not bool(x))}
+
+
+def transpose(C, M, accum, A, *, t0=False, complement=False, structure=False, replace=False):
+    """GrB_transpose(C, M, accum, A, desc) -- reference core/base.py:401-411; with INP0 transposed it is a plain copy."""
+    A1 = A if t0 else A.T()
+    if (C.nrows, C.ncols) != (A1.nrows, A1.ncols):
+        raise ValueError("GrB_DIMENSION_MISMATCH")
+    return _write_back(C, dict(A1.e), A.dtype, None if M is None else M.dup(), accum, complement, structure, replace)
+
+
+def ewise(C, M, accum, op, A, B, *, union, t0=False, t1=False, complement=False, structure=False, replace=False):
+    """GrB_Matrix_eWiseAdd / eWiseMult_BinaryOp -- reference core/matrix.py:1972-2108: the op on the intersection; eWiseAdd
+    also copies the entries present on one side only.  Comparison ops return BOOL."""
+    A1, B1 = (A.T() if t0 else A), (B.T() if t1 else B)
+    if (A1.nrows, A1.ncols) != (B1.nrows, B1.ncols) or (C.nrows, C.ncols) != (A1.nrows, A1.ncols):
+        raise ValueError("GrB_DIMENSION_MISMATCH")
+    D = unify(A.dtype, B.dtype)
+    cmp = op in COMPARE
+    f = COMPARE[op] if cmp else binary(op)
+    Z = np.dtype(np.bool_) if cmp else D
+    T = {}
+    with np.errstate(all="ignore"):
+        for k in set(A1.e) | set(B1.e):
+            if k in A1.e and k in B1.e:
+                T[k] = cast(f(cast(A1.e[k], D), cast(B1.e[k], D)), Z)
+            elif union:
+                T[k] = cast(cast(A1.e[k] if k in A1.e else B1.e[k], D), Z)
+    return _write_back(C, T, Z, None if M is None else M.dup(), accum, complement, structure, replace)
+
+
+def apply(C, M, accum, op, A, *, scalar=None, scalar_first=False, t0=False, complement=False, structure=False, replace=False):
+    """GrB_Matrix_apply (unary) / apply_BinaryOp1st / 2nd -- reference core/matrix.py:2440-2533; the pattern is A's."""
+    A1 = A.T() if t0 else A
+    D = A.dtype if scalar is None else unify(A.dtype, np.asarray(scalar).dtype if not isinstance(scalar, (bool, int, float)) else
+                                            (np.bool_ if isinstance(scalar, bool) else np.int64 if isinstance(scalar, int) else np.float64))
+    T = {}
+    with np.errstate(all="ignore"):
+        for k, v in A1.e.items():
+            x = cast(v, D)
+            if scalar is None:
+                T[k] = cast(UNARY[op](x), D)
+            else:
+                sc = cast(scalar, D)
+                T[k] = cast(binary(op)(sc, x) if scalar_first else binary(op)(x, sc), D)
+    return _write_back(C, T, D, None if M is None else M.dup(), accum, complement, structure, replace)
+
+
+def reduce_scalar(monoid, A):
+    """all entries folded in row-major order with the monoid; None for an empty matrix"""
+    keys = sorted(A.e)
+    if not keys:
+        return None
+    f = binary(monoid)
+    acc = A.e[keys[0]]
+    with np.errstate(all="ignore"):
+        for k in keys[1:]:
+            acc = cast(f(acc, A.e[k]), A.dtype)
+    return acc

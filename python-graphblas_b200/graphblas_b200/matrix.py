@@ -206,21 +206,43 @@ class Matrix(BaseType):
             return ScalarExpression(self.dtype, thunk)
         raise NotImplementedError("only scalar extraction A[i, j] is on this backend's path")
 
-    # ---- expressions
+    # ---- expressions (each is ONE C call; mask / accum / replace are applied by the library's write-back)
     def _dup_expr(self):
-        me = self
-
-        def run(out, mask, accum, desc):
-            if mask is not None or accum is not None:
-                raise NotImplementedError("masked / accumulated matrix assignment is outside this backend's path")
-            r, c, v = me.to_coo()
-            out.clear()
-            out.build(r, c, v)
-
-        return MatrixExpression("assign", None, [], dtype=self.dtype, nrows=self._nrows, ncols=self._ncols, custom=run)
+        return MatrixExpression("apply", "GrB_Matrix_apply", [self], op=operator.unary.identity[self.dtype],
+                                nrows=self._nrows, ncols=self._ncols, at=self._is_transposed)
 
     def _scalar_assign_expr(self, value):
         raise NotImplementedError("scalar assignment into a Matrix is outside this backend's path")
+
+    def ewise_add(self, other, op=None):
+        """reference core/matrix.py:1972-2056 (union of the patterns)"""
+        return _ewise(self, other, op, "ewise_add", "GrB_Matrix_eWiseAdd_BinaryOp", operator.monoid.plus)
+
+    def ewise_mult(self, other, op=None):
+        """reference core/matrix.py:2058-2108 (intersection of the patterns)"""
+        return _ewise(self, other, op, "ewise_mult", "GrB_Matrix_eWiseMult_BinaryOp", operator.binary.times)
+
+    def apply(self, op, right=None, *, left=None):
+        """reference core/matrix.py:2440-2533: unary op, or a binary op with the scalar bound first (left=) / second (right=)"""
+        return _apply(self, op, right, left)
+
+    def reduce_scalar(self, op=None, *, allow_empty=True):
+        """reference core/matrix.py:2703-2735"""
+        op = operator.monoid.plus if op is None else op
+        op = operator.get_typed_op(op, self.dtype, kind="monoid")
+        if op.opclass != "Monoid":
+            raise TypeError("reduce_scalar expects a Monoid")
+        me = self
+
+        def thunk():
+            x = op.return_type.ctype()
+            nv = GrB_Index()
+            call("GrB_cuda_Matrix_reduce", [ctypes.byref(x), op.return_type, None, op, me, ctypes.byref(nv)])
+            if nv.value == 0 and allow_empty:
+                return None
+            return x.value
+
+        return ScalarExpression(op.return_type, thunk)
 
     def mxv(self, other, op=None):
         """reference core/matrix.py:2233-2262"""
@@ -230,7 +252,7 @@ class Matrix(BaseType):
         """reference core/matrix.py:2294-2331"""
         return _mxm(self, other, op)
 
-    # ---- comparison (reference core/matrix.py:373-461); done on exported tuples
+    # ---- comparison: exactly the reference's recipe (core/matrix.py:373-415) -- eWiseMult(EQ) then reduce(LAND), on the device
     def isequal(self, other, *, check_dtype=False):
         if type(other) is not Matrix:
             raise TypeError(f"isequal expects a Matrix, got {type(other).__name__}")
@@ -238,9 +260,11 @@ class Matrix(BaseType):
             return False
         if self.shape != other.shape or self.nvals != other.nvals:
             return False
-        a, b = self.to_coo(), other.to_coo()
-        common = unify(self.dtype, other.dtype).np_type
-        return bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].astype(common), b[2].astype(common)))
+        common = unify(self.dtype, other.dtype)
+        matches = self.ewise_mult(other, operator.binary.eq[common]).new(BOOL)
+        if matches.nvals != self.nvals:
+            return False
+        return bool(matches.reduce_scalar(operator.monoid.land, allow_empty=False).value)
 
     def isclose(self, other, *, rel_tol=1e-7, abs_tol=0.0, check_dtype=False):
         if check_dtype and self.dtype != other.dtype:
@@ -307,23 +331,60 @@ class TransposedMatrix:
         return matmul(self, other)
 
     def _transpose_expr(self):
+        """C(mask, accum) << A.T  ->  GrB_transpose(C, mask, accum, A, desc), reference core/base.py:401-411"""
         me = self._matrix
+        return MatrixExpression("transpose", "GrB_transpose", [me], dtype=me.dtype, nrows=me._ncols, ncols=me._nrows)
 
-        def run(out, mask, accum, desc):
-            if mask is not None or accum is not None:
-                raise NotImplementedError("masked transpose is outside this backend's path")
-            Ap, Ai, Ax = me.to_csc()     # CSC of A is CSR of A'
-            new = Matrix.from_csr(Ap, Ai, Ax, me.dtype, ncols=me._nrows)
-            r, c, v = new.to_coo()
-            out.clear()
-            out.build(r, c, v)
+    def ewise_add(self, other, op=None):
+        return _ewise(self, other, op, "ewise_add", "GrB_Matrix_eWiseAdd_BinaryOp", operator.monoid.plus)
 
-        return MatrixExpression("transpose", None, [], dtype=me.dtype, nrows=me._ncols, ncols=me._nrows, custom=run)
+    def ewise_mult(self, other, op=None):
+        return _ewise(self, other, op, "ewise_mult", "GrB_Matrix_eWiseMult_BinaryOp", operator.binary.times)
+
+    def apply(self, op, right=None, *, left=None):
+        return _apply(self, op, right, left)
 
     def new(self, dtype=None, *, name=None):
         out = Matrix(dtype or self.dtype, self._nrows, self._ncols, name=name)
         out << self
         return out
+
+
+def _ewise(self, other, op, method_name, cfunc, default_op):
+    if not isinstance(other, (Matrix, TransposedMatrix)):
+        raise TypeError(f"{method_name} expects a Matrix, got {type(other).__name__}")
+    op = default_op if op is None else op
+    op = operator.get_typed_op(op, self.dtype, other.dtype, kind="binary")
+    if op.opclass == "Monoid":
+        op = op.binaryop
+    if op.opclass != "BinaryOp":
+        raise TypeError(f"{method_name} expects a BinaryOp or Monoid, got {op.opclass}")
+    expr = MatrixExpression(method_name, cfunc, [self, other], op=op, nrows=self._nrows, ncols=self._ncols,
+                            at=self._is_transposed, bt=other._is_transposed)
+    if self.shape != other.shape:
+        expr.new(name="")  # incompatible shape; raise now
+    return expr
+
+
+def _apply(self, op, right, left):
+    if right is None and left is None:
+        op = operator.get_typed_op(op, self.dtype, kind="unary")
+        return MatrixExpression("apply", "GrB_Matrix_apply", [self], op=op, nrows=self._nrows, ncols=self._ncols,
+                                at=self._is_transposed)
+    scalar = right if right is not None else left
+    sdt = lookup_dtype(np.asarray(scalar).dtype) if not isinstance(scalar, (int, float, bool)) else \
+        (BOOL if isinstance(scalar, bool) else INT64 if isinstance(scalar, int) else FP64)
+    op = operator.get_typed_op(op, self.dtype, sdt, kind="binary")
+    if op.opclass == "Monoid":
+        op = op.binaryop
+    me = self
+
+    def run(out, mask, accum, desc):
+        x = sdt.ctype(scalar)
+        call("GrB_cuda_Matrix_apply_binop", [out, mask, accum, op, me, ctypes.byref(x), sdt, 1 if left is not None else 0, desc])
+
+    return MatrixExpression("apply", None, [], dtype=op.return_type, nrows=self._nrows, ncols=self._ncols, custom=run,
+                            at=self._is_transposed)
 
 
 def _mxv(self, other, op):

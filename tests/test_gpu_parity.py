@@ -551,3 +551,87 @@ def test_mxm_optional_kernels_match_default(gb, opts):
             for k in opts:
                 gb.cuda.set_option(k, None)
         assert all(np.array_equal(x, y) for x, y in zip(want, got)), (opts, dtype, sr)
+
+
+def _spmat_equal(gbm, sp):
+    I, J, X = gbm.to_coo()
+    oi, oj, ox = sp.to_coo()
+    if not (np.array_equal(I.astype(np.int64), oi) and np.array_equal(J.astype(np.int64), oj)):
+        return False, f"pattern differs: {I.size} vs {oi.size} entries"
+    if not np.array_equal(X, ox.astype(X.dtype)):
+        return False, f"values differ: {X[:8]} vs {ox[:8]}"
+    return True, ""
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float64, np.int32, np.bool_])
+def test_matrix_elementwise_ops_vs_oracle(gb, dtype):
+    """GrB_transpose, GrB_Matrix_apply (+ bind 1st / 2nd), GrB_Matrix_eWiseAdd / eWiseMult, reduce to scalar and the
+    reference's own Matrix.isequal recipe (eWiseMult(EQ) + reduce(LAND)) -- all on the device, with mask / accum / replace through
+    the common write-back, against the dict oracle (exact)."""
+    rng = np.random.default_rng(17)
+    for trial, (m, n, nnz) in enumerate([(1, 1, 1), (7, 5, 12), (60, 80, 900), (300, 300, 4000)]):
+        ra, ca = H.random_coo(rng, m, n, nnz)
+        rb, cb = H.random_coo(rng, m, n, nnz)
+        rc, cc = H.random_coo(rng, m, n, max(1, nnz // 2))
+        rm, cm = H.random_coo(rng, m, n, nnz)
+        va, vb, vc = (H.random_values(rng, r.size, dtype) for r in (ra, rb, rc))
+        vm = rng.integers(0, 2, rm.size).astype(np.int64)
+        A, B = H.gb_matrix(gb, ra, ca, va, m, n), H.gb_matrix(gb, rb, cb, vb, m, n)
+        Ao, Bo = S.SpMat.from_coo(ra, ca, va, m, n, dtype), S.SpMat.from_coo(rb, cb, vb, m, n, dtype)
+        Mo = S.SpMat.from_coo(rm, cm, vm, m, n, np.int64)
+        M = H.gb_matrix(gb, rm, cm, vm, m, n)
+        accum_name = "lor" if dtype == np.bool_ else "plus"
+        variants = [dict(), dict(mask="S"), dict(mask="V", complement=True, replace=True), dict(accum=accum_name),
+                    dict(mask="S", accum=accum_name, replace=True)]
+        ops = [("ewise_add", "lor" if dtype == np.bool_ else "plus"), ("ewise_mult", "land" if dtype == np.bool_ else "times"),
+               ("ewise_add", "min"), ("ewise_mult", "eq"), ("ewise_add", "first")]
+        for var in variants:
+            def run(expr, oracle_fn, out_dtype=dtype, shape=(m, n)):
+                C = H.gb_matrix(gb, rc, cc, vc, m, n) if shape == (m, n) else gb.Matrix(out_dtype, *shape)
+                Co = S.SpMat.from_coo(rc, cc, vc, m, n, dtype) if shape == (m, n) else S.SpMat(shape[0], shape[1], out_dtype)
+                if out_dtype != dtype and shape == (m, n):
+                    C, Co = gb.Matrix(out_dtype, m, n), S.SpMat(m, n, out_dtype)
+                kw, okw = {}, {}
+                if "mask" in var and shape == (m, n):
+                    mk = M.S if var["mask"] == "S" else M.V
+                    kw["mask"] = ~mk if var.get("complement") else mk
+                    okw.update(structure=var["mask"] == "S", complement=bool(var.get("complement")))
+                    omask = Mo
+                else:
+                    omask = None
+                if var.get("accum"):
+                    kw["accum"] = getattr(gb.binary, var["accum"])
+                if var.get("replace") and "mask" in kw:
+                    kw["replace"] = True
+                    okw["replace"] = True
+                (C(**kw) if kw else C).update(expr) if kw else C.update(expr)
+                oracle_fn(Co, omask, var.get("accum"), **okw)
+                ok, msg = _spmat_equal(C, Co)
+                assert ok, (dtype, trial, var, msg)
+            for method, opname in ops:
+                cmp = opname in S.COMPARE
+                run(getattr(A, method)(B, getattr(gb.binary, opname)),
+                    lambda Co, Mm, acc, **k: S.ewise(Co, Mm, acc, opname, Ao, Bo, union=method == "ewise_add", **k),
+                    out_dtype=np.bool_ if cmp else dtype)
+            for uop in (["identity", "lnot"] if dtype == np.bool_ else ["ainv", "abs", "identity"]):
+                run(A.apply(getattr(gb.unary, uop)), lambda Co, Mm, acc, **k: S.apply(Co, Mm, acc, uop, Ao, **k))
+            if dtype != np.bool_:
+                run(A.apply(gb.binary.minus, right=3), lambda Co, Mm, acc, **k: S.apply(Co, Mm, acc, "minus", Ao, scalar=dtype(3), **k))
+                run(A.apply(gb.binary.minus, left=3), lambda Co, Mm, acc, **k: S.apply(Co, Mm, acc, "minus", Ao, scalar=dtype(3), scalar_first=True, **k))
+            run(A, lambda Co, Mm, acc, **k: S.apply(Co, Mm, acc, "identity", Ao, **k))      # C(...) << A
+            if m == n:
+                run(A.T, lambda Co, Mm, acc, **k: S.transpose(Co, Mm, acc, Ao, **k))
+                run(A.T.ewise_mult(B, getattr(gb.binary, "land" if dtype == np.bool_ else "times")),
+                    lambda Co, Mm, acc, **k: S.ewise(Co, Mm, acc, "land" if dtype == np.bool_ else "times", Ao, Bo, union=False, t0=True, **k))
+        # transpose of a non-square matrix into a fresh output, reduce, isequal
+        At = A.T.new()
+        ok, msg = _spmat_equal(At, Ao.T())
+        assert ok, msg
+        assert At.T.new().isequal(A) and A.isequal(A.dup()) and (not A.isequal(B) or (np.array_equal(ra, rb) and np.array_equal(ca, cb) and np.array_equal(va, vb)))
+        for mon in (["lor", "land"] if dtype == np.bool_ else ["plus", "max", "min"]):
+            got = A.reduce_scalar(getattr(gb.monoid, mon)).new().value
+            want = S.reduce_scalar(mon, Ao)
+            assert got == want, (dtype, mon, got, want)
+        assert gb.Matrix(dtype, 3, 4).reduce_scalar(gb.monoid.lor if dtype == np.bool_ else gb.monoid.plus).new().value is None
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        gb.Matrix(dtype, 3, 4).ewise_add(gb.Matrix(dtype, 4, 3))
