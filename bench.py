@@ -139,9 +139,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ the reference arm (CPU)
-def cpu_mxm_sample(indptr, indices, values, n, budget_s=15.0, seed=0):
+def cpu_mxm_sample(indptr, indices, values, n, budget_s=15.0, seed=0, rows_hint=None):
     """Times the oracle port (OpenMP Gustavson SpGEMM) on a random row sample sized for ~budget_s of CPU work.
-    Returns (nnz_out_per_s, description, threads)."""
+    Returns (nnz_out_per_s, description, threads, rows_used, seconds).  `rows_hint` skips the sizing search."""
     from oracle import bigref as R
 
     A = R.BigMat(indptr, indices, values, n, n)
@@ -158,17 +158,17 @@ def cpu_mxm_sample(indptr, indices, values, n, budget_s=15.0, seed=0):
 
     # grow the sample until it costs a meaningful fraction of the budget (per-call set-up of the dense accumulators --
     # O(threads x ncols) -- would otherwise dominate a small sample and understate the CPU)
-    m = min(n, 1 << 15)
+    m = min(n, rows_hint if rows_hint else 1 << 15)
     while True:
         rows = rng.choice(n, size=m, replace=False)
         As = sub(rows)
         t0 = time.perf_counter()
         T = R.mxm_T("plus_times", As, A)
         dt = time.perf_counter() - t0
-        if dt >= budget_s / 3 or m >= n:
+        if rows_hint or dt >= budget_s / 3 or m >= n:
             break
         m = int(min(n, max(m * 2, m * (budget_s / max(dt, 1e-3)) * 0.7)))
-    return T.nvals / dt, f"{m} random rows of A (of {n}) times full A, {T.nvals} output entries in {dt:.2f} s", R.num_threads()
+    return T.nvals / dt, f"{m} random rows of A (of {n}) times full A, {T.nvals} output entries in {dt:.2f} s", R.num_threads(), m, dt
 
 
 def run_reference(args):
@@ -187,15 +187,18 @@ def run_reference(args):
     np.add.at(indptr, r + 1, 1)
     np.cumsum(indptr, out=indptr)
     vals = np.random.default_rng(43).random(r.size).astype(np.float32)
-    rates = []
+    rates, secs, hint = [], [], None
     for s in range(args.warmup + args.steps):
-        rate, desc, threads = cpu_mxm_sample(indptr, c, vals, n, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)), seed=s)
+        # the first (warm-up) step sizes the sample for the per-step budget; the timed steps reuse that size with fresh rows
+        rate, desc, threads, hint, dt = cpu_mxm_sample(indptr, c, vals, n, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)),
+                                                       seed=s, rows_hint=hint)
         if s >= args.warmup:
             rates.append(rate)
+            secs.append(dt)
     value = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": "mxm nnz-out/s (R-MAT plus_times fp32)", "value": value, "unit": "nnz-out/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"R-MAT scale-{scale} (0.45,0.15,0.15,0.25) ef16 seed42 A.mxm(A) plus_times fp32", "sample": desc},
         "cpu_baseline": {"value": value, "unit": "nnz-out/s", "cores": threads, "kind": "port", "sample": desc,
@@ -557,7 +560,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         try:
             hp, hc, hv = indptr.cpu().numpy(), cols.cpu().numpy().astype(np.int64), vals.cpu().numpy()
-            rate, desc, threads = cpu_mxm_sample(hp, hc, hv, n, budget_s=args.cpu_budget)
+            rate, desc, threads, _, _ = cpu_mxm_sample(hp, hc, hv, n, budget_s=args.cpu_budget)
             cpu = {"value": rate, "unit": "nnz-out/s", "cores": threads, "kind": "port", "sample": desc,
                    "note": "SuiteSparse:GraphBLAS unavailable on this box -- baseline is the oracle restatement (OpenMP Gustavson SpGEMM)"}
         except Exception as exc:   # never lose the GPU numbers because the CPU leg failed
