@@ -101,29 +101,67 @@ def values_torch(nnz, seed, dtype, device="cuda"):
 
 # ------------------------------------------------------------------ clocks sampling during the timed region
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 100 ms DURING the timed region.  NVML is queried in-process (pynvml): spawning
+    `nvidia-smi` every 200 ms initialises NVML and enumerates all GPUs of the box each time, which on a busy 8-GPU host takes
+    hundreds of ms under the driver lock and stalled this process's own CUDA calls (one run measured 168 ms per step for 56 ms of
+    kernels).  nvidia-smi remains the fallback when pynvml is unavailable."""
+
     def __init__(self, gpu_index=0):
         self.samples, self.reasons = [], set()
         self._stop = threading.Event()
         self.gpu = gpu_index
         self.sm_max = None
+        self.source = "nvml"
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                ids = [int(t) for t in vis.split(",")]
+                phys = ids[gpu_index] if gpu_index < len(ids) else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
         self._t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _sample_nvml(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for nm, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                        ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.sm_max = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.sm_max = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1 if self._h is not None else 0.5)
 
     def __enter__(self):
         self._t.start()
@@ -135,7 +173,7 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------ the reference arm (CPU)

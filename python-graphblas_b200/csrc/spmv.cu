@@ -320,31 +320,60 @@ template <typename T> __global__ void fill_value_kernel(T *__restrict__ p, T v, 
     for (; i < n; i += stride) p[i] = v;
 }
 
+// one product of the push traversal: mask tested in-register, then the atomic monoid combine
+template <typename SR, typename T>
+__device__ __forceinline__ void push_edge(const SR &sr, int64_t k, T uv, const int32_t *__restrict__ colidx, const T *__restrict__ avals,
+                                          bool flip, const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
+                                          uint8_t *__restrict__ t_present) {
+    const int32_t j = colidx[k];
+    if (mask && ((mask[j] != 0) == mask_comp)) return;   // mask applied in-register before the write
+    if (SR::kAddIsAny && !sr.reads_a() && !sr.reads_b()) {
+        t_present[j] = 1;   // any_pair: value is the constant 1 written by the fill
+    } else {
+        const T av = sr.reads_a() ? avals[k] : one_of<T>();
+        const T p = flip ? sr.mul(uv, av) : sr.mul(av, uv);
+        atomic_combine(sr, &t_vals[j], p);
+        t_present[j] = 1;
+    }
+}
+
+// A warp per frontier vertex.  A vertex with >= PUSH_HEAVY_DEG edges would keep ONE warp busy for milliseconds (the BFS source of
+// a Graph500 R-MAT has ~10^5 neighbours): such vertices are only queued here and the whole grid then walks each of their
+// adjacency lists together (spmspv_push_heavy_kernel).
+constexpr int64_t PUSH_HEAVY_DEG = 4096;
 template <typename SR, typename T>
 __global__ void __launch_bounds__(256)
 spmspv_push_kernel(SR sr, const int32_t *__restrict__ frontier, int64_t n_frontier, const int64_t *__restrict__ rowptr,
                    const int32_t *__restrict__ colidx, const T *__restrict__ avals, const T *__restrict__ u, bool flip,
-                   const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
-                   uint8_t *__restrict__ t_present) {
+                   const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals, uint8_t *__restrict__ t_present,
+                   int32_t *__restrict__ heavy, unsigned long long *__restrict__ heavy_count) {
     const int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t f = w; f < n_frontier; f += nw) {
         const int32_t i = frontier[f];
+        const int64_t b = rowptr[i], e = rowptr[i + 1];
+        if (heavy && e - b >= PUSH_HEAVY_DEG) {
+            if (lane == 0) heavy[atomicAdd(heavy_count, 1ull)] = i;
+            continue;
+        }
+        const T uv = sr.reads_b() ? u[i] : one_of<T>();
+        for (int64_t k = b + lane; k < e; k += 32) push_edge<SR, T>(sr, k, uv, colidx, avals, flip, mask, mask_comp, t_vals, t_present);
+    }
+}
+template <typename SR, typename T>
+__global__ void __launch_bounds__(256)
+spmspv_push_heavy_kernel(SR sr, const int32_t *__restrict__ heavy, const unsigned long long *__restrict__ heavy_count,
+                         const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const T *__restrict__ avals,
+                         const T *__restrict__ u, bool flip, const uint8_t *__restrict__ mask, bool mask_comp,
+                         T *__restrict__ t_vals, uint8_t *__restrict__ t_present) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    const unsigned long long nh = *heavy_count;
+    for (unsigned long long h = 0; h < nh; h++) {
+        const int32_t i = heavy[h];
         const T uv = sr.reads_b() ? u[i] : one_of<T>();
         const int64_t b = rowptr[i], e = rowptr[i + 1];
-        for (int64_t k = b + lane; k < e; k += 32) {
-            int32_t j = colidx[k];
-            if (mask && ((mask[j] != 0) == mask_comp)) continue;  // mask applied in-register before the write
-            T av = sr.reads_a() ? avals[k] : one_of<T>();
-            T p = flip ? sr.mul(uv, av) : sr.mul(av, uv);
-            if (SR::kAddIsAny && !sr.reads_a() && !sr.reads_b()) {
-                t_present[j] = 1;  // any_pair: value is the constant 1 written by the fill
-            } else {
-                atomic_combine(sr, &t_vals[j], p);
-                t_present[j] = 1;
-            }
-        }
+        for (int64_t k = b + tid; k < e; k += nt) push_edge<SR, T>(sr, k, uv, colidx, avals, flip, mask, mask_comp, t_vals, t_present);
     }
 }
 
@@ -473,7 +502,7 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
 template <typename SR, typename T>
 static GrB_Info run_push(const SR &sr, const CsrArrays &A, int64_t arows, int64_t out_len, const T *avals, const T *u,
                          const uint8_t *up, int64_t u_nvals, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
-                         uint8_t *t_present, std::string *err) {
+                         uint8_t *t_present, int64_t nnz_total, std::string *err) {
     CUDA_TRY(err, cudaMemsetAsync(t_present, 0, (size_t)(out_len > 0 ? out_len : 1), g_stream));
     {
         T init = (SR::kAddIsAny && !sr.reads_a() && !sr.reads_b()) ? one_of<T>() : sr.identity();
@@ -483,9 +512,12 @@ static GrB_Info run_push(const SR &sr, const CsrArrays &A, int64_t arows, int64_
     }
     if (u_nvals == 0 || arows == 0) return GrB_SUCCESS;
     int32_t *frontier = dev_alloc_t<int32_t>((size_t)u_nvals);
-    unsigned long long *counter = dev_alloc_t<unsigned long long>(1);
-    if (!frontier || !counter) { dev_free(frontier); dev_free(counter); return set_error(err, GrB_OUT_OF_MEMORY, "frontier"); }
-    CUDA_TRY(err, cudaMemsetAsync(counter, 0, 8, g_stream));
+    unsigned long long *counter = dev_alloc_t<unsigned long long>(2);   // [0] frontier cursor, [1] heavy-vertex cursor
+    // at most nnz / PUSH_HEAVY_DEG vertices can be heavy
+    const int64_t heavy_cap = std::min<int64_t>(u_nvals, nnz_total / PUSH_HEAVY_DEG + 1);
+    int32_t *heavy = dev_alloc_t<int32_t>((size_t)heavy_cap);
+    if (!frontier || !counter || !heavy) { dev_free(frontier); dev_free(counter); dev_free(heavy); return set_error(err, GrB_OUT_OF_MEMORY, "frontier"); }
+    CUDA_TRY(err, cudaMemsetAsync(counter, 0, 16, g_stream));
     {
         int blocks = (int)std::min<int64_t>((arows + 255) / 256, (int64_t)g_num_sms * 16);
         LAUNCH_NOTE("compact_frontier");
@@ -494,10 +526,14 @@ static GrB_Info run_push(const SR &sr, const CsrArrays &A, int64_t arows, int64_
     {
         int blocks = (int)std::min<int64_t>((u_nvals + 7) / 8, (int64_t)g_num_sms * 32);
         LAUNCH_NOTE("spmspv_push");
-        spmspv_push_kernel<SR, T><<<blocks, 256, 0, g_stream>>>(sr, frontier, u_nvals, A.ptr, A.idx, avals, u, flip, mask, mask_comp, t_vals, t_present);
+        spmspv_push_kernel<SR, T><<<blocks, 256, 0, g_stream>>>(sr, frontier, u_nvals, A.ptr, A.idx, avals, u, flip, mask, mask_comp, t_vals, t_present, heavy, counter + 1);
+    }
+    if (nnz_total >= PUSH_HEAVY_DEG) {   // a heavy vertex can exist: the whole grid walks each queued adjacency list (no host sync: the count is read on the device)
+        LAUNCH_NOTE("spmspv_push_heavy");
+        spmspv_push_heavy_kernel<SR, T><<<g_num_sms * 4, 256, 0, g_stream>>>(sr, heavy, counter + 1, A.ptr, A.idx, avals, u, flip, mask, mask_comp, t_vals, t_present);
     }
     cudaError_t e = cudaGetLastError();
-    dev_free(frontier); dev_free(counter);
+    dev_free(frontier); dev_free(counter); dev_free(heavy);
     CUDA_TRY(err, e);
     return GrB_SUCCESS;
 }
@@ -551,7 +587,7 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             const uint8_t *up = (u->nvals == u->n) ? nullptr : u->present;
             if (push)
                 info = run_push<SRT, T>(sr, A->csr, A->nrows, a.out_len, (const T *)av, (const T *)uv, u->present,
-                                        u->nvals, kflip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, a.err);
+                                        u->nvals, kflip, a.mask, a.mask_comp, (T *)a.t_vals, a.t_present, A->nvals, a.err);
             else {
                 VecEpi<T> epi;
                 memset(&epi, 0, sizeof epi);

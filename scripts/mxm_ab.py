@@ -16,13 +16,9 @@ A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
 sr = gb.semiring.plus_times
 SETS = [
     {},
-    {"spgemm_streams": "0"},
-    {"spgemm_stream_split_bin": "6"},
-    {"spgemm_stream_split_bin": "7"},
-    {"spgemm_stream_split_bin": "9"},
-    {"spgemm_stream_split_bin": "10"},
+    {"spgemm_batch_cas": "0"},
     {},
-    {"spgemm_streams": "0"},
+    {"spgemm_batch_cas": "0"},
 ]
 if len(sys.argv) > 2:
     SETS = [json.loads(a) for a in sys.argv[2:]]
