@@ -340,7 +340,7 @@ __device__ __forceinline__ void push_edge(const SR &sr, int64_t k, T uv, const i
 // A warp per frontier vertex.  A vertex with >= PUSH_HEAVY_DEG edges would keep ONE warp busy for milliseconds (the BFS source of
 // a Graph500 R-MAT has ~10^5 neighbours): such vertices are only queued here and the whole grid then walks each of their
 // adjacency lists together (spmspv_push_heavy_kernel).
-constexpr int64_t PUSH_HEAVY_DEG = 4096;
+constexpr int64_t PUSH_HEAVY_DEG = 4096, PUSH_GRID_DEG = 32768;
 template <typename SR, typename T>
 __global__ void __launch_bounds__(256)
 spmspv_push_kernel(SR sr, const int32_t *__restrict__ frontier, int64_t n_frontier, const int64_t *__restrict__ rowptr,
@@ -369,10 +369,20 @@ spmspv_push_heavy_kernel(SR sr, const int32_t *__restrict__ heavy, const unsigne
                          T *__restrict__ t_vals, uint8_t *__restrict__ t_present) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
     const unsigned long long nh = *heavy_count;
+    // heavy vertices (< PUSH_GRID_DEG edges): one CTA each, round-robin -- a frontier can hold hundreds of them
+    for (unsigned long long h = blockIdx.x; h < nh; h += gridDim.x) {
+        const int32_t i = heavy[h];
+        const int64_t b = rowptr[i], e = rowptr[i + 1];
+        if (e - b >= PUSH_GRID_DEG) continue;
+        const T uv = sr.reads_b() ? u[i] : one_of<T>();
+        for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) push_edge<SR, T>(sr, k, uv, colidx, avals, flip, mask, mask_comp, t_vals, t_present);
+    }
+    // the few giant ones: the whole grid walks each adjacency list together
     for (unsigned long long h = 0; h < nh; h++) {
         const int32_t i = heavy[h];
-        const T uv = sr.reads_b() ? u[i] : one_of<T>();
         const int64_t b = rowptr[i], e = rowptr[i + 1];
+        if (e - b < PUSH_GRID_DEG) continue;
+        const T uv = sr.reads_b() ? u[i] : one_of<T>();
         for (int64_t k = b + tid; k < e; k += nt) push_edge<SR, T>(sr, k, uv, colidx, avals, flip, mask, mask_comp, t_vals, t_present);
     }
 }
