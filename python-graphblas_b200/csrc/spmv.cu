@@ -601,7 +601,12 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             else {
                 VecEpi<T> epi;
                 memset(&epi, 0, sizeof epi);
-                if (a.epi) {   // pull kernels finish every row exactly once: the write-back is applied there, in registers
+                // pull kernels finish every row exactly once: the write-back is applied there, in registers -- except for 8-byte
+                // values without a mask, where the segmented kernel (whose row emission would be uncoalesced with the write-back
+                // fused) plus the separate O(n) write-back pass beats the fused merge-path kernel (SSSP: 455 vs 580 us)
+                const bool unfuse = a.epi && !a.mask && !a.epi->has_mask && sizeof(T) >= 8 && !strcmp(opt_get("spmv", "auto"), "auto") &&
+                                    A->nvals >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_unfuse_wide", 1) != 0;
+                if (a.epi && !unfuse) {
                     epi.active = 1;
                     epi.c_vals = (const T *)a.epi->c_vals; epi.c_present = a.epi->c_present; epi.mask = a.epi->mask;
                     epi.has_mask = a.epi->has_mask; epi.comp = a.epi->comp; epi.replace = a.epi->replace; epi.accum = a.epi->accum;
