@@ -265,15 +265,29 @@ __device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
     for (int q = 0; q < NBINS - 1; q++) b += (c > s.maxcount[q]);
     return b;
 }
+__host__ __device__ __forceinline__ int64_t gtable_size_of(int64_t c) { return (2 * c + 1024) & ~(int64_t)3; }   // multiple of 4 keeps the value array 16-byte aligned
+// bin_counts[0..NBINS) = rows per bin; bin_counts[NBINS] = total global-table entries the rows of the last bin need
 __global__ void bin_count_kernel(BinSpec spec, int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ bin_counts) {
     __shared__ unsigned int s[NBINS];
+    __shared__ unsigned long long s_g;
     if (threadIdx.x < NBINS) s[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_g = 0;
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nrows; i += stride) atomicAdd(&s[bin_of(spec, cnt[i])], 1u);
+    for (; i < nrows; i += stride) {
+        const int64_t c = cnt[i];
+        const int b = bin_of(spec, c);
+        atomicAdd(&s[b], 1u);
+        if (b == NBINS - 1) atomicAdd(&s_g, (unsigned long long)gtable_size_of(c));
+    }
     __syncthreads();
     if (threadIdx.x < NBINS && s[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+    if (threadIdx.x == 0 && s_g) atomicAdd(&bin_counts[NBINS], s_g);
+}
+struct BinCursors { unsigned long long v[NBINS]; };
+__global__ void bin_cursors_kernel(BinCursors c, unsigned long long *__restrict__ cursors) {
+    if (threadIdx.x < NBINS) cursors[threadIdx.x] = c.v[threadIdx.x];
 }
 // two-level: CTA-local histogram + one global atomic per (CTA, bin) reserves a contiguous range
 __global__ void bin_fill_kernel(BinSpec spec, int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ cursors,
@@ -1017,9 +1031,8 @@ spgemm_group_elect_kernel(SR sr, const int64_t *__restrict__ g_start, const int3
 __global__ void gtable_sizes_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt,
                                     int64_t *__restrict__ sizes) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int64_t c = cnt[rows[i]];
-    sizes[i] = (2 * c + 1024) & ~(int64_t)3;   // multiple of 4 keeps the value array 16-byte aligned
+    if (i > n) return;
+    sizes[i] = i < n ? gtable_size_of(cnt[rows[i]]) : 0;   // sizes[n]: pad slot of the in-place exclusive scan
 }
 __global__ void i64_copy_kernel(int64_t *dst, const int64_t *src, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1091,35 +1104,39 @@ struct Bins {
     int32_t *rows = nullptr;           // row ids grouped by bin
     unsigned long long count[NBINS];   // rows per bin
     unsigned long long start[NBINS];   // offset of each bin inside rows[]
+    unsigned long long gtable_entries = 0;   // global-table entries the rows of the last bin need in total
     BinSpec spec;
 };
 
 static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const int64_t *cnt, std::string *err) {
     bins->spec = make_bin_spec(entry_bytes);
-    unsigned long long *d = dev_alloc_t<unsigned long long>(2 * NBINS);
+    unsigned long long *d = dev_alloc_t<unsigned long long>(2 * NBINS + 2);
     bins->rows = dev_alloc_t<int32_t>((size_t)(nrows > 0 ? nrows : 1));
     if (!d || !bins->rows) { dev_free(d); dev_free(bins->rows); bins->rows = nullptr; return set_error(err, GrB_OUT_OF_MEMORY, "spgemm bins"); }
-    cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 2 * NBINS, g_stream);
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (2 * NBINS + 2), g_stream);
     int blocks = (int)std::min<int64_t>((nrows + 255) / 256 + 1, (int64_t)g_num_sms * 8);
     {
         LAUNCH_NOTE("spgemm_bin_count");
         bin_count_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d);
     }
-    cudaMemcpyAsync(bins->count, d, sizeof(unsigned long long) * NBINS, cudaMemcpyDeviceToHost, g_stream);
-    cudaStreamSynchronize(g_stream);
-    unsigned long long off = 0, cursors[NBINS];
+    unsigned long long hcount[NBINS + 1];
+    cudaMemcpyAsync(hcount, d, sizeof(unsigned long long) * (NBINS + 1), cudaMemcpyDeviceToHost, g_stream);
+    cudaStreamSynchronize(g_stream);   // the ONE host round trip of the binning: grid sizes of the per-bin launches
+    BinCursors cur;
+    unsigned long long off = 0;
     for (int b = 0; b < NBINS; b++) {
+        bins->count[b] = hcount[b];
         bins->start[b] = off;
-        cursors[b] = off;
+        cur.v[b] = off;
         if (b > 0) off += bins->count[b];
     }
-    cudaMemcpyAsync(d + NBINS, cursors, sizeof(cursors), cudaMemcpyHostToDevice, g_stream);
+    bins->gtable_entries = hcount[NBINS];
     {
         LAUNCH_NOTE("spgemm_bin_fill");
-        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d + NBINS, bins->rows);
+        bin_cursors_kernel<<<1, 32, 0, g_stream>>>(cur, d + NBINS + 1);   // cursors by value: no host buffer to keep alive, no sync
+        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d + NBINS + 1, bins->rows);
     }
     cudaError_t e = cudaGetLastError();
-    cudaStreamSynchronize(g_stream);   // `cursors` is a host stack array read by the async copy
     dev_free(d);
     CUDA_TRY(err, e);
     return GrB_SUCCESS;
@@ -1210,12 +1227,35 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
             kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
         } else {
-            // rows whose bound exceeds the largest shared table: global-memory tables, in batches that fit a budget
+            // rows whose bound exceeds the largest shared table: global-memory tables.  The total table size came back with the
+            // bin counts, so the usual case is fully asynchronous: sizes -> device scan -> one launch, no host round trip
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
+            const int64_t tot_all = (int64_t)bins.gtable_entries;
+            if (tot_all <= budget_entries) {
+                int64_t *doffs = dev_alloc_t<int64_t>((size_t)n + 1);
+                const size_t bytes = Table::kPacked ? (size_t)tot_all * 8 : (size_t)tot_all * 4 + (NUMERIC ? (size_t)tot_all * sizeof(T) + 16 : 0);
+                unsigned char *gt = (unsigned char *)dev_alloc(bytes);
+                GrB_Info ginfo = GrB_SUCCESS;
+                if (!doffs || !gt) ginfo = set_error(err, GrB_OUT_OF_MEMORY, "global hash tables (%lld entries)", (long long)tot_all);
+                if (!ginfo) {
+                    note_launch("gtable_sizes");
+                    gtable_sizes_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, g_stream>>>(rows, n, a.cnt, doffs);
+                    ginfo = exclusive_scan_i64(doffs, n + 1, err);
+                }
+                if (!ginfo) {
+                    LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)n, 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
+                    cudaError_t ge = cudaGetLastError();
+                    if (ge != cudaSuccess) ginfo = cuda_fail(err, ge, "global-table spgemm kernel");
+                }
+                dev_free(doffs); dev_free(gt);   // stream-ordered
+                return ginfo;
+            }
+            // larger than the budget: batches sized on the host
             int64_t *sizes = dev_alloc_t<int64_t>((size_t)n + 1);
             if (!sizes) return set_error(err, GrB_OUT_OF_MEMORY, "global table sizes");
             note_launch("gtable_sizes");
-            gtable_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(rows, n, a.cnt, sizes);
+            gtable_sizes_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, g_stream>>>(rows, n, a.cnt, sizes);
             std::vector<int64_t> hs((size_t)n + 1);
             cudaMemcpyAsync(hs.data(), sizes, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, g_stream);
             cudaStreamSynchronize(g_stream);
@@ -1378,8 +1418,11 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     bool onepass = false;
     if (!info && !symbolic_only && total_flops > 0) {
         const char *mode = opt_get("spgemm_mode", "auto");
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
+        static size_t total_b = 0;   // device memory size: asked once (cudaMemGetInfo is a driver round trip)
+        if (total_b == 0) {
+            size_t free_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+        }
         const double need = 2.0 * (double)total_flops * (double)(4 + es);
         const double avail = (double)total_b * 0.9 - (double)GrB_cuda_memory_in_use();
         onepass = !strcmp(mode, "onepass") || (!strcmp(mode, "auto") && need < 0.8 * avail);
