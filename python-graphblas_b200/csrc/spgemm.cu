@@ -21,6 +21,7 @@
 //
 // Serves GrB_mxm: reference graphblas/core/matrix.py:2319-2328 (call assembled at core/base.py:496-503).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <vector>
 
 #include "grb_ops.cuh"
@@ -1524,7 +1525,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
                 note_launch("split_flops");
                 split_flops_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, R, gbig);
                 size_t tb = 0;
-                cub::CountingInputIterator<int> it(0);
+                thrust::counting_iterator<int> it(0);
                 cub::DeviceSelect::If(nullptr, tb, it, gsrows, d_count, (int)p.m, SmallRowPred{flops, R}, g_stream);
                 tmp = dev_alloc(tb);
                 if (!tmp) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group scratch");

@@ -256,42 +256,56 @@ spmv_rowwarp_kernel(SR sr, int64_t nrows, const int64_t *__restrict__ rowptr, co
                     const T *__restrict__ avals, const T *__restrict__ x, const uint8_t *__restrict__ xp, bool flip,
                     const uint8_t *__restrict__ mask, bool mask_comp, T *__restrict__ t_vals,
                     uint8_t *__restrict__ t_present, VecEpi<T> epi) {
+    // A warp takes 32 consecutive rows: every lane first filters ITS row (mask, row length) and writes the empty result of a
+    // masked-out / empty row itself -- coalesced, and without a dependent load chain per skipped row (in a bottom-up BFS step
+    // most rows are skipped) -- then the warp walks the rows that are left, one at a time, all lanes on one row.
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = w; i < nrows; i += nw) {
-        if (mask) {
-            bool m = (mask[i] != 0) != mask_comp;
-            if (!m) {  // masked out: T(i) is irrelevant, the row is never read
-                if (lane == 0) epi_write(epi, i, T(), 0, t_vals, t_present);
-                continue;
+    for (int64_t base = w * 32; base < nrows; base += nw * 32) {
+        const int64_t mine = base + lane;
+        long long b = 0, e = 0;
+        bool need = false;
+        if (mine < nrows) {
+            const bool m = mask ? ((mask[mine] != 0) != mask_comp) : true;
+            if (m) {
+                b = rowptr[mine];
+                e = rowptr[mine + 1];
+                need = e > b;
             }
+            if (!need) epi_write(epi, mine, T(), 0, t_vals, t_present);   // masked out (T(i) irrelevant, row never read) or no entries
         }
-        const int64_t b = rowptr[i], e = rowptr[i + 1];
-        T acc = sr.identity();
-        int has = 0;
-        for (int64_t k = b + lane; k < e; k += 32) {
-            int32_t c = colidx[k];
-            bool ph = XFULL ? true : (xp[c] != 0);
-            if (ph) {
-                T av = sr.reads_a() ? avals[k] : one_of<T>();
-                T xv = sr.reads_b() ? x[c] : one_of<T>();
-                T p = flip ? sr.mul(xv, av) : sr.mul(av, xv);
-                acc = has ? sr.add(acc, p) : p;
-                has = 1;
+        unsigned todo = __ballot_sync(FULL, need);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t rb = __shfl_sync(FULL, b, src), re = __shfl_sync(FULL, e, src);
+            T acc = sr.identity();
+            int has = 0;
+            for (int64_t k = rb + lane; k < re; k += 32) {
+                int32_t c = colidx[k];
+                bool ph = XFULL ? true : (xp[c] != 0);
+                if (ph) {
+                    T av = sr.reads_a() ? avals[k] : one_of<T>();
+                    T xv = sr.reads_b() ? x[c] : one_of<T>();
+                    T p = flip ? sr.mul(xv, av) : sr.mul(av, xv);
+                    acc = has ? sr.add(acc, p) : p;
+                    has = 1;
+                }
+                if (SR::kAddIsAny && __any_sync(__activemask(), has)) break;
             }
-            if (SR::kAddIsAny && __any_sync(__activemask(), has)) break;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            T ov = shfl_down_any(acc, o);
-            int oh = __shfl_down_sync(0xffffffffu, has, o);
-            if (oh) {
-                acc = has ? sr.add(acc, ov) : ov;
-                has = 1;
+            for (int o = 16; o > 0; o >>= 1) {
+                T ov = shfl_down_any(acc, o);
+                int oh = __shfl_down_sync(FULL, has, o);
+                if (oh) {
+                    acc = has ? sr.add(acc, ov) : ov;
+                    has = 1;
+                }
             }
+            if (lane == 0) epi_write(epi, base + src, acc, has, t_vals, t_present);
         }
-        if (lane == 0) epi_write(epi, i, acc, has, t_vals, t_present);
     }
 }
 
@@ -412,8 +426,8 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
     const char *method = opt_get("spmv", "auto");
     bool use_rowwarp = !strcmp(method, "rowwarp") || (!strcmp(method, "auto") && mask != nullptr);
     if (use_rowwarp) {
-        int64_t warps_needed = mrows;
-        int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)g_num_sms * 32);
+        int64_t warps_needed = (mrows + 31) / 32;   // a warp filters 32 rows at a time
+        int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, (int64_t)g_num_sms * 32));
         LAUNCH_NOTE("spmv_rowwarp");
         if (xp) spmv_rowwarp_kernel<SR, T, false><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present, epi);
         else spmv_rowwarp_kernel<SR, T, true><<<blocks, 256, 0, g_stream>>>(sr, mrows, M.ptr, M.idx, avals, x, xp, flip, mask, mask_comp, t_vals, t_present, epi);

@@ -20,6 +20,7 @@
 // Algorithmic bytes per multiply (adapted: the row pointers are not read): nnz*(4 + rho*s_val) + nnz/8
 // + nonempty_rows*4 + ncols*s_x + nrows*(s_y + 1).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 
@@ -85,7 +86,7 @@ static GrB_Info ensure_seg(CsrArrays &c, int64_t nrows, int64_t nnz, std::string
         note_launch("seg_flags");
         seg_flag_kernel<<<blocks, 256, 0, g_stream>>>(nrows, c.ptr, reinterpret_cast<unsigned int *>(c.seg_flags));
         size_t tb = 0;
-        cub::CountingInputIterator<int> it(0);
+        thrust::counting_iterator<int> it(0);
         cub::DeviceSelect::If(nullptr, tb, it, c.seg_rows, d_count, (int)nrows, SegRowNonEmpty{c.ptr}, g_stream);
         tmp = dev_alloc(tb);
         if (!tmp) info = set_error(err, GrB_OUT_OF_MEMORY, "segmented SpMV metadata scratch");
