@@ -20,7 +20,13 @@
 constexpr int SPMV_BLOCK = 256;
 
 // items per thread: odd, so that the per-thread walk over shared memory (stride IPT words) is bank-conflict free
-template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? 5 : 7); };
+#ifndef SPMV_IPT4
+#define SPMV_IPT4 7
+#endif
+#ifndef SPMV_IPT8
+#define SPMV_IPT8 5
+#endif
+template <typename T> struct SpmvCfg { static constexpr int IPT = (sizeof(T) >= 8 ? SPMV_IPT8 : SPMV_IPT4); };
 
 // (row, value, has) triple of a partially reduced row; combine = reduce-by-key, associative
 template <typename T> struct Carry { int row; int has; T val; };
