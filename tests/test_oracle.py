@@ -231,3 +231,66 @@ def test_inner_outer_reference_known_answers():
     want = S.SpMat(7, 7, np.int64)
     S.mxm(want, None, None, "plus_times", v.as_col(), v.as_row())
     assert out.e == want.e and len(out.e) == 16 and int(out.e[(4, 4)]) == 4 and int(out.e[(6, 1)]) == 0
+
+
+def test_matrix_elementwise_oracle_vs_scipy():
+    """The oracle's matrix element-wise restatement (transpose / eWiseAdd / eWiseMult / apply / reduce), which the GPU tests use as
+    the checker for SURVEY 8(f1), cross-checked against scipy.sparse on seeded inputs (exactly representable values)."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(23)
+    m, n = 40, 55
+    def rand():
+        key = np.unique(rng.integers(0, m * n, 400))
+        r, c = key // n, key % n
+        v = rng.integers(-5, 6, r.size).astype(np.float64)
+        return S.SpMat.from_coo(r, c, v, m, n, np.float64), sp.csr_matrix((v, (r, c)), shape=(m, n))
+    (Ao, As), (Bo, Bs) = rand(), rand()
+
+    def same(o, s_):
+        s_ = s_.tocoo()
+        want = {(int(i), int(j)): float(v) for i, j, v in zip(s_.row, s_.col, s_.data)}
+        got = {k: float(v) for k, v in o.e.items()}
+        return got == want
+
+    C = S.SpMat(n, m, np.float64); S.transpose(C, None, None, Ao)
+    assert same(C, As.T.tocsr())
+    # eWiseAdd(plus): scipy drops the explicit zeros that cancel; compare on the union pattern with values
+    C = S.SpMat(m, n, np.float64); S.ewise(C, None, None, "plus", Ao, Bo, union=True)
+    dense = As.toarray() + Bs.toarray()
+    pattern = (As != 0).toarray() | (Bs != 0).toarray() | np.isin(np.arange(m * n).reshape(m, n), [i * n + j for (i, j) in set(Ao.e) | set(Bo.e)])
+    assert set(C.e) == set(Ao.e) | set(Bo.e) and all(float(v) == dense[k] for k, v in C.e.items()) and pattern.sum() >= len(C.e)
+    C = S.SpMat(m, n, np.float64); S.ewise(C, None, None, "times", Ao, Bo, union=False)
+    prod = As.toarray() * Bs.toarray()
+    assert set(C.e) == set(Ao.e) & set(Bo.e) and all(float(v) == prod[k] for k, v in C.e.items())
+    C = S.SpMat(m, n, np.float64); S.apply(C, None, None, "ainv", Ao)
+    assert set(C.e) == set(Ao.e) and all(float(v) == -float(Ao.e[k]) for k, v in C.e.items())
+    C = S.SpMat(m, n, np.float64); S.apply(C, None, None, "minus", Ao, scalar=np.float64(3), scalar_first=True)
+    assert all(float(v) == 3 - float(Ao.e[k]) for k, v in C.e.items())
+    assert float(S.reduce_scalar("plus", Ao)) == float(As.sum()) and float(S.reduce_scalar("max", Ao)) == float(max(Ao.e.values()))
+    # mask + accum through the common write-back: C<M.S>(plus) = A'  on a square case
+    Sq, Ss = S.SpMat.from_coo([0, 1, 2], [1, 2, 0], [1.0, 2.0, 3.0], 3, 3, np.float64), None
+    Cq = S.SpMat.from_coo([1, 0], [0, 0], [10.0, 20.0], 3, 3, np.float64)
+    Mq = S.SpMat.from_coo([1, 2], [0, 1], [0, 1], 3, 3, np.int64)
+    S.transpose(Cq, Mq, "plus", Sq, structure=True)
+    assert {k: float(v) for k, v in Cq.e.items()} == {(1, 0): 11.0, (0, 0): 20.0, (2, 1): 2.0}
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` prints ONE JSON line with the keys the driver reads (small scale so it runs in seconds)."""
+    import json
+    import pathlib
+    import subprocess
+    import sys
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--scale", "12", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=str(root))
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stderr[-2000:]
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "nnz-out/s" and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
