@@ -226,6 +226,47 @@ class Matrix(BaseType):
         """reference core/matrix.py:2440-2533: unary op, or a binary op with the scalar bound first (left=) / second (right=)"""
         return _apply(self, op, right, left)
 
+    def power(self, n, op=None):
+        """reference core/matrix.py:2840-2905 (+ `_power`, :101-164): A^n over a semiring by repeated squaring, every product one
+        GrB_mxm on the device; n = 0 gives the diagonal matrix of the multiply's monoid identity."""
+        from .exceptions import DimensionMismatch
+
+        if self._nrows != self._ncols:
+            raise DimensionMismatch(f"power only works for square Matrix; shape is {self.shape}")
+        if isinstance(n, (bool, np.bool_)) or not isinstance(n, (int, np.integer)):
+            raise TypeError(f"n must be a nonnegative integer; got bad type: {type(n)}")
+        N = int(n)
+        if N < 0:
+            raise ValueError(f"n must be a nonnegative integer; got: {N}")
+        op = operator.semiring.plus_times if op is None else op
+        op = operator.get_typed_op(op, self.dtype, kind="semiring")
+        if op.opclass != "Semiring":
+            raise TypeError(f"power expects a Semiring, got {op.opclass}")
+        ident = _MULT_IDENTITY.get(op.parent.binaryop.name)
+        if N == 0 and ident is None:
+            raise ValueError(f"Binary operator of {op} semiring does not have a monoid with an identity. When n=0, the result is a "
+                             "diagonal matrix with values equal to the identity of the binaryop, so the binaryop must be associated "
+                             "with a monoid.")
+        me = self
+
+        def run(out, mask, accum, desc):
+            if N == 0:
+                idx = np.arange(me._nrows, dtype=np.uint64)
+                P = Matrix.from_coo(idx, idx, np.full(me._nrows, ident(me.dtype.np_type), dtype=me.dtype.np_type),
+                                    nrows=me._nrows, ncols=me._ncols, dtype=me.dtype)
+            else:
+                P, square, k = None, me, N
+                while True:
+                    if k & 1:
+                        P = square if P is None else P.mxm(square, op).new()
+                    k >>= 1
+                    if k == 0:
+                        break
+                    square = square.mxm(square, op).new()
+            call("GrB_Matrix_apply", [out, mask, accum, operator.unary.identity[P.dtype], P, desc])
+
+        return MatrixExpression("power", None, [], dtype=op.return_type, nrows=self._nrows, ncols=self._ncols, custom=run)
+
     def reduce_scalar(self, op=None, *, allow_empty=True):
         """reference core/matrix.py:2703-2735"""
         op = operator.monoid.plus if op is None else op
@@ -348,6 +389,24 @@ class TransposedMatrix:
         out = Matrix(dtype or self.dtype, self._nrows, self._ncols, name=name)
         out << self
         return out
+
+
+def _np_limit(kind):
+    def f(np_type):
+        dt = np.dtype(np_type)
+        if dt == np.bool_:
+            return kind == "max"          # identity of min on BOOL (= land) is True, of max (= lor) is False
+        if dt.kind == "f":
+            return np.inf if kind == "max" else -np.inf
+        info = np.iinfo(dt)
+        return info.max if kind == "max" else info.min
+    return f
+
+
+# identity of the monoid the semiring's multiply belongs to (what A.power(0) puts on the diagonal)
+_MULT_IDENTITY = {"times": lambda t: 1, "plus": lambda t: 0, "min": _np_limit("max"), "max": _np_limit("min"),
+                  "land": lambda t: True, "lor": lambda t: False, "lxor": lambda t: False, "lxnor": lambda t: True,
+                  "any": lambda t: 0}
 
 
 def _ewise(self, other, op, method_name, cfunc, default_op):

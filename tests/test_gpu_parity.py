@@ -635,3 +635,37 @@ def test_matrix_elementwise_ops_vs_oracle(gb, dtype):
         assert gb.Matrix(dtype, 3, 4).reduce_scalar(gb.monoid.lor if dtype == np.bool_ else gb.monoid.plus).new().value is None
     with pytest.raises(gb.exceptions.DimensionMismatch):
         gb.Matrix(dtype, 3, 4).ewise_add(gb.Matrix(dtype, 4, 3))
+
+
+def test_matrix_power(gb):
+    """SURVEY 8(f3): Matrix.power -- reference tests/test_matrix.py:4379-4405 (`A.power(i)` equals the i-fold product, INT64 wraps;
+    min_plus powers; n = 0 is the diagonal of the multiply's identity; argument errors)."""
+    d = G.load(G.A_M)
+    A = _obj(gb, G.A_M)
+    Ab = R.BigMat.from_coo(d["rows"], d["cols"], d["vals"], 7, 7)
+    Pb = Ab
+    for i in range(1, 50):
+        ok, msg = H.mat_equal(A.power(i).new(), Pb)
+        assert ok, (i, msg)
+        Pb = R.mxm_T("plus_times", Pb, Ab)
+    Pb = Ab
+    for i in range(1, 10):
+        ok, msg = H.mat_equal(A.power(i, gb.semiring.min_plus).new(), Pb)
+        assert ok, (i, msg)
+        Pb = R.mxm_T("min_plus", Pb, Ab)
+    I0, J0, X0 = A.power(0).new().to_coo()
+    assert np.array_equal(I0, np.arange(7)) and np.array_equal(J0, np.arange(7)) and np.array_equal(X0, np.ones(7, dtype=X0.dtype))
+    _, _, Xm = A.power(0, gb.semiring.min_plus).new().to_coo()
+    assert np.array_equal(Xm, np.zeros(7, dtype=Xm.dtype))
+    # accumulate into an existing matrix: C(plus) << A.power(2)  ==  C + A*A
+    C = A.dup()
+    C(gb.binary.plus) << A.power(2)
+    want = A.dup()
+    want(gb.binary.plus) << A.mxm(A)
+    assert C.isequal(want)
+    with pytest.raises(ValueError):
+        A.power(-1)
+    with pytest.raises(TypeError):
+        A.power(1.5)
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        gb.Matrix(gb.dtypes.INT64, 3, 4).power(2)
