@@ -669,3 +669,28 @@ def test_matrix_power(gb):
         A.power(1.5)
     with pytest.raises(gb.exceptions.DimensionMismatch):
         gb.Matrix(gb.dtypes.INT64, 3, 4).power(2)
+
+
+def test_empty_operands_everywhere(gb):
+    """Empty matrices / vectors through every entry point added around the multiply (transpose, apply, eWise, reduce, isequal,
+    power, inner, outer, mxm / mxv / vxm): results are empty objects of the right shape, never an error."""
+    E = gb.Matrix(gb.dtypes.FP64, 3, 4)
+    B = gb.Matrix.from_coo([0, 2], [1, 3], [1.5, -2.0], nrows=3, ncols=4)
+    Et = E.T.new()
+    assert Et.shape == (4, 3) and Et.nvals == 0
+    assert E.apply(gb.unary.ainv).new().nvals == 0 and E.apply(gb.binary.plus, right=1.0).new().nvals == 0
+    assert E.ewise_add(B).new().isequal(B) and B.ewise_add(E).new().isequal(B)
+    assert E.ewise_mult(B).new().nvals == 0 and B.ewise_mult(E, gb.binary.eq).new().nvals == 0
+    assert E.isequal(gb.Matrix(gb.dtypes.FP64, 3, 4)) and not E.isequal(B)
+    assert E.reduce_scalar(gb.monoid.plus).new().value is None
+    C = B.dup()
+    C(mask=B.S, replace=True) << E                      # assignment of an empty matrix under a mask with replace: everything goes
+    assert C.nvals == 0
+    S3 = gb.Matrix(gb.dtypes.INT64, 3, 3)
+    assert S3.power(3).new().nvals == 0 and S3.power(0).new().nvals == 3
+    assert S3.mxm(S3).new().nvals == 0 and E.T.mxm(B).new().nvals == 0 and B.T.mxm(E).new().nvals == 0
+    ev, v = gb.Vector(gb.dtypes.FP64, 4), gb.Vector.from_coo([1, 3], [2.0, 5.0], size=4)
+    assert ev.inner(v).new().value is None and v.inner(ev).new().value is None and ev.inner(ev).new().value is None
+    assert ev.outer(v).new().nvals == 0 and v.outer(ev).new().nvals == 0 and v.outer(v).new().nvals == 4
+    assert ev._as_matrix().shape == (4, 1) and ev._as_matrix().nvals == 0
+    assert B.mxv(ev).new().nvals == 0 and E.mxv(v).new().nvals == 0 and gb.Vector(gb.dtypes.FP64, 3).vxm(B).new().nvals == 0
