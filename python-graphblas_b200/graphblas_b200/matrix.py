@@ -267,6 +267,16 @@ class Matrix(BaseType):
 
         return MatrixExpression("power", None, [], dtype=op.return_type, nrows=self._nrows, ncols=self._ncols, custom=run)
 
+    def reduce_rowwise(self, op=None):
+        """reference core/matrix.py:2600-2650 (GrB_Matrix_reduce_Monoid): w(i) = (+)_j A(i, j) over the entries of row i; rows
+        without entries give no entry.  Run as ONE pull SpMV with the semiring <monoid>_first against an all-present vector:
+        first(a, x) = a, so the multiply passes A's values through and the vector's values are never read."""
+        return _reduce_to_vector(self, op, "reduce_rowwise")
+
+    def reduce_columnwise(self, op=None):
+        """reference core/matrix.py:2652-2701: the row-wise reduction of the transpose (GrB_DESC_T0)"""
+        return _reduce_to_vector(self.T, op, "reduce_columnwise")
+
     def reduce_scalar(self, op=None, *, allow_empty=True):
         """reference core/matrix.py:2703-2735"""
         op = operator.monoid.plus if op is None else op
@@ -385,6 +395,12 @@ class TransposedMatrix:
     def apply(self, op, right=None, *, left=None):
         return _apply(self, op, right, left)
 
+    def reduce_rowwise(self, op=None):
+        return _reduce_to_vector(self, op, "reduce_rowwise")
+
+    def reduce_columnwise(self, op=None):
+        return _reduce_to_vector(self._matrix, op, "reduce_columnwise")
+
     def new(self, dtype=None, *, name=None):
         out = Matrix(dtype or self.dtype, self._nrows, self._ncols, name=name)
         out << self
@@ -407,6 +423,19 @@ def _np_limit(kind):
 _MULT_IDENTITY = {"times": lambda t: 1, "plus": lambda t: 0, "min": _np_limit("max"), "max": _np_limit("min"),
                   "land": lambda t: True, "lor": lambda t: False, "lxor": lambda t: False, "lxnor": lambda t: True,
                   "any": lambda t: 0}
+
+
+def _reduce_to_vector(self, op, method_name):
+    op = operator.monoid.plus if op is None else op
+    op = operator.get_typed_op(op, self.dtype, kind="monoid")
+    if op.opclass != "Monoid":
+        raise TypeError(f"{method_name} expects a Monoid, got {op.opclass}")
+    sr = getattr(operator.semiring, f"{op.parent.name}_first", None)
+    if sr is None or op.type not in sr:
+        raise NotImplementedError(f"no builtin semiring {op.parent.name}_first[{op.type.name}] behind {method_name}")
+    ones = Vector(self.dtype, self._ncols)
+    ones[:] = 1
+    return VectorExpression(method_name, "GrB_mxv", [self, ones], op=sr[op.type], size=self._nrows, at=self._is_transposed)
 
 
 def _ewise(self, other, op, method_name, cfunc, default_op):

@@ -694,3 +694,35 @@ def test_empty_operands_everywhere(gb):
     assert ev.outer(v).new().nvals == 0 and v.outer(ev).new().nvals == 0 and v.outer(v).new().nvals == 4
     assert ev._as_matrix().shape == (4, 1) and ev._as_matrix().nvals == 0
     assert B.mxv(ev).new().nvals == 0 and E.mxv(v).new().nvals == 0 and gb.Vector(gb.dtypes.FP64, 3).vxm(B).new().nvals == 0
+
+
+def test_matrix_reduce_to_vector(gb):
+    """Matrix.reduce_rowwise / reduce_columnwise (reference core/matrix.py:2600-2701) through the <monoid>_first SpMV: against numpy
+    on seeded matrices (exact), rows / columns without entries absent from the result, mask + accum through the common write-back."""
+    rng = np.random.default_rng(29)
+    for dtype in (np.int64, np.float64, np.int32):
+        m, n = 70, 45
+        r, c = H.random_coo(rng, m, n, 600)
+        v = H.random_values(rng, r.size, dtype)
+        A = H.gb_matrix(gb, r, c, v, m, n)
+        for mon, fn in (("plus", np.add), ("max", np.maximum), ("min", np.minimum), ("times", np.multiply)):
+            for axis, size, idx in ((0, m, r), (1, n, c)):
+                want = {}
+                for i, x in zip(idx.tolist(), v.tolist()):
+                    want[i] = dtype(x) if i not in want else dtype(fn(want[i], dtype(x)))
+                red = (A.reduce_rowwise if axis == 0 else A.reduce_columnwise)(getattr(gb.monoid, mon)).new()
+                gi, gv = red.to_coo()
+                assert red.size == size and np.array_equal(gi, np.array(sorted(want))), (dtype, mon, axis)
+                assert np.array_equal(gv, np.array([want[k] for k in sorted(want)], dtype=gv.dtype)), (dtype, mon, axis)
+        # the transposed view reduces the other way round; accumulate into an existing vector under a mask
+        gi, gv = A.T.reduce_rowwise(gb.monoid.plus).new().to_coo()
+        ci, cv = A.reduce_columnwise(gb.monoid.plus).new().to_coo()
+        assert np.array_equal(gi, ci) and np.array_equal(gv, cv)
+        w = gb.Vector.from_coo(np.arange(m), np.ones(m, dtype=dtype), size=m)
+        w(gb.binary.plus) << A.reduce_rowwise(gb.monoid.plus)
+        base = A.reduce_rowwise(gb.monoid.plus).new()
+        bi, bv = base.to_coo()
+        wi, wv = w.to_coo()
+        exp = np.ones(m, dtype=dtype); exp[bi] += bv
+        assert np.array_equal(wi, np.arange(m)) and np.array_equal(wv, exp)
+    assert gb.Matrix(gb.dtypes.FP64, 5, 6).reduce_rowwise().new().nvals == 0
