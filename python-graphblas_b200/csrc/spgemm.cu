@@ -122,22 +122,6 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
             }
         }
     }
-    // packed tables: the first probe of a product as a bare CAS (issued for a whole batch before any result is looked at, so
-    // several atomics per thread are in flight), and the rest of the probe sequence for the ones that did not settle
-    __device__ __forceinline__ unsigned long long first_cas(int j, T p, unsigned h) { return atomicCAS(&ent[h], HASH_EMPTY64, pack_entry<T>(j, p)); }
-    __device__ __forceinline__ int settle(const SR &sr, int j, T p, unsigned h, unsigned long long cur) {
-        if (cur == HASH_EMPTY64) return 1;
-        const unsigned long long mine = pack_entry<T>(j, p);
-        while (true) {
-            if ((int)(cur >> 32) == j) {
-                atomic_combine(sr, reinterpret_cast<T *>(&ent[h]), p);
-                return 0;
-            }
-            h = (h + 1 == size) ? 0 : h + 1;
-            cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
-            if (cur == HASH_EMPTY64) return 1;
-        }
-    }
     // ---- masked product (C<M> = A*B, M not complemented): the row's table is pre-loaded with the mask row's columns,
     // each tagged MASK_FLAG ("allowed, nothing accumulated yet").  A product whose column is not in the table is dropped
     // before any arithmetic is stored; the first product that hits a column clears the tag (idempotent atomicAnd),
@@ -256,8 +240,7 @@ static BinSpec make_bin_spec(size_t entry_bytes) {
         if (s.maxcount[b] < s.maxcount[b - 1]) s.maxcount[b] = s.maxcount[b - 1];   // a tighter factor must not reorder the bins
     }
     s.maxcount[NBINS - 1] = INT64_MAX;
-    s.flags = (opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0) | (opt_get_int("spgemm_elect", 0) != 0 ? 2 : 0) |
-              (opt_get_int("spgemm_batch_cas", 0) != 0 ? 4 : 0);
+    s.flags = (opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0) | (opt_get_int("spgemm_elect", 0) != 0 ? 2 : 0);
     return s;
 }
 __device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
@@ -479,38 +462,12 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
                 }
                 p += 32;
             }
-            bool batched = false;
-            if constexpr (Table::kPacked) batched = (flags & 5) == 5 && !mk.Mp;
-            if (batched) {
-              if constexpr (Table::kPacked) {
-                // all first-probe CAS of the batch are issued before the first result is examined: UNROLL atomics in flight
-                // per thread instead of one (the insert is latency-bound, most of all on global-memory tables)
-                T prs[UNROLL];
-                unsigned hh[UNROLL];
-                unsigned long long cur[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    prs[u] = T();
-                    hh[u] = 0;
-                    cur[u] = 0;
-                    if (jj[u] != HASH_EMPTY) {
-                        prs[u] = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                        hh[u] = hash_slot(jj[u], tab.size);
-                        cur[u] = tab.first_cas(jj[u], prs[u], hh[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++)
-                    if (jj[u] != HASH_EMPTY) local_new += tab.settle(sr, jj[u], prs[u], hh[u], cur[u]);
-              }
-            } else {
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    if (jj[u] == HASH_EMPTY) continue;
-                    T pr = T();
-                    if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                    local_new += mk.Mp ? tab.accumulate_masked(sr, jj[u], pr) : tab.insert(sr, jj[u], pr);
-                }
+            for (int u = 0; u < UNROLL; u++) {
+                if (jj[u] == HASH_EMPTY) continue;
+                T pr = T();
+                if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                local_new += mk.Mp ? tab.accumulate_masked(sr, jj[u], pr) : tab.insert(sr, jj[u], pr);
             }
         }
         __syncthreads();   // s_* arrays are rewritten by the next chunk

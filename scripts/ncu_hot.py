@@ -3,7 +3,7 @@ import csv, gzip, io, sys
 rows = list(csv.reader(io.TextIOWrapper(gzip.open(sys.argv[1]))))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-body = rows[2:]
+body = [r for r in rows[2:] if len(r) == len(hdr) and (r[ix['# Samples']] or '0').isdigit()]   # a multi-kernel dump repeats the header
 tot = sum(int(r[ix['# Samples']] or 0) for r in body)
 execd = sum(int(r[ix['Instructions Executed']] or 0) for r in body)
 print("total samples", tot, "warp instructions executed", execd)

@@ -531,8 +531,8 @@ def test_inner_outer(gb):
 
 
 @pytest.mark.parametrize("opts", [{"spgemm_elect": "1"}, {"spgemm_group": "1"}, {"spgemm_group": "1", "spgemm_group_g": "512", "spgemm_group_r": "64"},
-                                  {"spgemm_cas_first": "0"}, {"spgemm_batch_cas": "1"}, {"spgemm_mode": "twopass"}, {"spgemm_gtable_entries": "30000"}],
-                         ids=["elect", "group", "group-small", "probe-first", "batched-cas", "twopass", "gtable-batches"])
+                                  {"spgemm_cas_first": "0"}, {"spgemm_mode": "twopass"}, {"spgemm_gtable_entries": "30000"}],
+                         ids=["elect", "group", "group-small", "probe-first", "twopass", "gtable-batches"])
 def test_mxm_optional_kernels_match_default(gb, opts):
     """The optional SpGEMM insert kernels (atomics-free owner election per row / per group of rows, probe-before-CAS, two-pass)
     must produce exactly the default kernels' result: integer values bit-exact, same pattern, on an R-MAT product whose
