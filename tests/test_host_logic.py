@@ -1,0 +1,82 @@
+"""CPU-only: the host mirror's argument logic that decides WHICH C call is made -- descriptor names, mask flags, dtype
+unification, operator strings -- pinned to the reference's rules (no GPU, no compute calls; the .so is only dlopen'ed for its
+data symbols)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import graphblas_b200 as gb
+from graphblas_b200 import base, dtypes, operator
+
+
+def test_descriptor_names_follow_reference_table():
+    """reference core/descriptor.py:51-84: the 32 (replace, structure, complement, T0, T1) combinations map to GrB_DESC_<R><S><C><T0><T1>
+    and the all-default one to NULL."""
+    assert base.descriptor_lookup() is None
+    seen = set()
+    for r, s, c, t0, t1 in itertools.product([False, True], repeat=5):
+        d = base.descriptor_lookup(output_replace=r, mask_structure=s, mask_complement=c, transpose_first=t0, transpose_second=t1)
+        if not any((r, s, c, t0, t1)):
+            assert d is None
+            continue
+        want = "GrB_DESC_" + ("R" if r else "") + ("S" if s else "") + ("C" if c else "") + ("T0" if t0 else "") + ("T1" if t1 else "")
+        assert d.gb_name == want and d.gb_obj is not None
+        seen.add(d.gb_name)
+    assert len(seen) == 31 and {"GrB_DESC_RSC", "GrB_DESC_ST0", "GrB_DESC_T0T1", "GrB_DESC_RSCT0T1"} <= seen
+    # reference core/descriptor.py:122-125 / tests/test_matrix.py:4329-4331: unknown options are an error on a non-suitesparse backend
+    with pytest.raises(ValueError, match="Extra descriptor options not possible"):
+        base.descriptor_lookup(nthreads=4)
+
+
+def test_mask_flag_algebra():
+    """reference core/mask.py:133-203: .S / .V and their complements carry (complement, structure, value) flags; ~~m is m."""
+    class P:   # stands in for a Matrix / Vector: masks only hold a reference
+        name, _carg = "p", None
+    s, v = base.StructuralMask(P), base.ValueMask(P)
+    assert (s.structure, s.value, s.complement) == (True, False, False)
+    assert (v.structure, v.value, v.complement) == (False, True, False)
+    assert ((~s).structure, (~s).complement) == (True, True) and ((~v).value, (~v).complement) == (True, True)
+    assert type(~~s) is base.StructuralMask and type(~~v) is base.ValueMask and (~~s).parent is P
+
+
+def test_dtype_unify_is_numpy_promotion():
+    """reference core/dtypes.py:552-568: unify(a, b) = numpy promote_types on the 11 builtin types (BOOL absorbs into the other)."""
+    all_types = [dtypes.BOOL, dtypes.INT8, dtypes.INT16, dtypes.INT32, dtypes.INT64, dtypes.UINT8, dtypes.UINT16, dtypes.UINT32,
+                 dtypes.UINT64, dtypes.FP32, dtypes.FP64]
+    for a, b in itertools.product(all_types, repeat=2):
+        want = np.promote_types(a.np_type, b.np_type)
+        assert dtypes.unify(a, b) == dtypes.lookup_dtype(want), (a, b)
+    assert dtypes.unify(dtypes.INT64, dtypes.UINT64) == dtypes.FP64 and dtypes.unify(dtypes.BOOL, dtypes.INT8) == dtypes.INT8
+    for key, want in ((int, dtypes.INT64), (float, dtypes.FP64), (bool, dtypes.BOOL), ("FP32", dtypes.FP32), (np.int16, dtypes.INT16),
+                      ("GrB_UINT8", dtypes.UINT8), (np.dtype("float64"), dtypes.FP64)):
+        assert dtypes.lookup_dtype(key) is want
+    assert dtypes._INDEX is dtypes.UINT64   # GrB_Index = uint64_t (reference core/dtypes.py:389-396)
+
+
+def test_operator_strings_and_typed_lookup():
+    """reference core/operator/utils.py:60-157 + base.py string parsing: "+" / "plus" / "min.+" / "plus_times[FP32]"."""
+    operator.initialize()
+    assert operator.get_typed_op("+", dtypes.INT64, kind="binary").gb_name == "GrB_PLUS_INT64"
+    assert operator.get_typed_op("plus", dtypes.FP32, kind="binary").gb_name == "GrB_PLUS_FP32"
+    assert operator.get_typed_op("min.+", dtypes.INT32, dtypes.INT32, kind="semiring").gb_name == "GrB_MIN_PLUS_SEMIRING_INT32"
+    assert operator.get_typed_op("plus_times[FP32]", dtypes.INT8, kind="semiring").gb_name == "GrB_PLUS_TIMES_SEMIRING_FP32"
+    assert operator.get_typed_op(gb.monoid.plus, dtypes.INT16, kind="monoid").gb_name == "GrB_PLUS_MONOID_INT16"
+    # two operand types unify before the lookup
+    assert operator.get_typed_op(gb.semiring.plus_times, dtypes.INT32, dtypes.FP32, kind="semiring").type == dtypes.FP64
+    assert operator.get_typed_op(gb.binary.minus, dtypes.UINT8, dtypes.INT8, kind="binary").type == dtypes.INT16
+    with pytest.raises(ValueError, match="Unknown"):
+        operator.get_typed_op("no_such_op", dtypes.INT64, kind="binary")
+    with pytest.raises(TypeError):
+        operator.get_typed_op(3.5, dtypes.INT64, kind="binary")
+    # every hot semiring exists for every type it is defined on
+    for name in ("plus_times", "min_plus", "plus_second", "any_pair", "max_plus", "plus_first", "min_first", "max_first"):
+        sr = getattr(gb.semiring, name)
+        for t in (dtypes.INT8, dtypes.INT64, dtypes.UINT32, dtypes.FP32, dtypes.FP64):
+            assert t in sr, (name, t)
+    assert dtypes.BOOL in gb.semiring.lor_land and gb.semiring.lor_land[dtypes.BOOL].return_type == dtypes.BOOL
+    # the multiply's monoid identity table behind Matrix.power(0)
+    from graphblas_b200.matrix import _MULT_IDENTITY
+
+    assert _MULT_IDENTITY["times"](np.int64) == 1 and _MULT_IDENTITY["plus"](np.float32) == 0
+    assert _MULT_IDENTITY["min"](np.int8) == 127 and _MULT_IDENTITY["max"](np.float64) == -np.inf and "pair" not in _MULT_IDENTITY
