@@ -202,6 +202,36 @@ def mxm_T(semiring, A: BigMat, B: BigMat, rows=None):
     return BigMat(Cp, Cj, Cx, r1 - r0, B.ncols)
 
 
+def mxm_baseline_f32(A: BigMat, B: BigMat, *, hash_max_flops=4096, indices32=None):
+    """The CPU BASELINE of bench.py (not the parity oracle): plus_times fp32 A*B in one numeric pass, unsorted rows, 32-bit
+    indices, hash accumulator for rows with <= hash_max_flops products and the dense Gustavson workspace above (see the C
+    side).  Returns (nvals, seconds of the multiply itself, staging arrays) -- the timed region covers the per-row flop
+    bound, its prefix and the numeric pass; converting the operands to 32-bit indices is input preparation, as importing a
+    matrix is for the library under test.  `indices32` = (Aj32, Bj32) reuses converted index arrays."""
+    import time
+
+    L = lib()
+    Aj = A.indices.astype(np.int32) if indices32 is None else indices32[0]
+    Bj = B.indices.astype(np.int32) if indices32 is None else indices32[1]
+    Ax, Bx = np.ascontiguousarray(A.values, dtype=np.float32), np.ascontiguousarray(B.values, dtype=np.float32)
+    m = A.nrows
+    t0 = time.perf_counter()
+    flops = np.empty(m + 1, dtype=np.int64)
+    L.oracle_row_flops32(ctypes.c_int64(0), ctypes.c_int64(m), _p(A.indptr), _p(Aj), _p(B.indptr), _p(flops))
+    flops[m] = 0
+    Sp = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(flops[:m], out=Sp[1:])
+    total = int(Sp[-1])
+    Cj = np.empty(max(total, 1), dtype=np.int32)
+    Cx = np.empty(max(total, 1), dtype=np.float32)
+    row_nnz = np.empty(m, dtype=np.int64)
+    rc = L.oracle_mxm_baseline_f32(ctypes.c_int64(0), ctypes.c_int64(m), ctypes.c_int64(B.ncols), _p(A.indptr), _p(Aj), _p(Ax),
+                                   _p(B.indptr), _p(Bj), _p(Bx), _p(Sp), _p(Cj), _p(Cx), _p(row_nnz), ctypes.c_int64(hash_max_flops))
+    dt = time.perf_counter() - t0
+    assert rc == 0, rc
+    return int(row_nnz.sum()), dt, (Sp, row_nnz, Cj, Cx)
+
+
 # --------------------------------------------------------------------------- write-back
 def _accum_np(name, c, t):
     with np.errstate(all="ignore"):

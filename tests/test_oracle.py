@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import golden_cases as G
+import helpers as H
 from oracle import bigref as R
 from oracle import semantics as S
 
@@ -294,3 +295,22 @@ def test_bench_reference_arm_json_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "nnz-out/s" and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_fast_cpu_baseline_matches_oracle():
+    """bench.py's CPU baseline (one pass, unsorted rows, hash / dense accumulators, 32-bit indices) computes exactly what the
+    sorted two-pass parity oracle computes: same row counts, and per row the same (column, value) set -- for both accumulators."""
+    r, c, n = H.rmat_edges(12, a=0.45, b=0.15, c=0.15, seed=42)
+    ip = np.zeros(n + 1, dtype=np.int64)
+    ip[1:] = np.cumsum(np.bincount(r, minlength=n))
+    vals = np.random.default_rng(43).integers(1, 4, r.size).astype(np.float32)   # small integers: fp32 sums are exact
+    A = R.BigMat(ip, c, vals, n, n)
+    T = R.mxm_T("plus_times", A, A)
+    for hm in (0, 64, 1 << 20):   # dense workspace only / mixed / hash only
+        nv, dt, (Sp, rn, Cj, Cx) = R.mxm_baseline_f32(A, A, hash_max_flops=hm)
+        assert nv == T.nvals and dt > 0 and np.array_equal(rn, np.diff(T.indptr)), hm
+        for i in range(n):
+            s, e = int(Sp[i]), int(Sp[i]) + int(rn[i])
+            o = np.argsort(Cj[s:e])
+            assert np.array_equal(Cj[s:e][o].astype(np.int64), T.indices[T.indptr[i]:T.indptr[i + 1]]), (hm, i)
+            assert np.array_equal(Cx[s:e][o], T.values[T.indptr[i]:T.indptr[i + 1]]), (hm, i)
