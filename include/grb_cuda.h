@@ -61,6 +61,8 @@ typedef struct GrB_Semiring_opaque *GrB_Semiring;
 typedef struct GrB_Descriptor_opaque *GrB_Descriptor;
 typedef struct GrB_Matrix_opaque *GrB_Matrix;
 typedef struct GrB_Vector_opaque *GrB_Vector;
+typedef struct GrB_Scalar_opaque *GrB_Scalar;
+typedef struct GrB_IndexUnaryOp_opaque *GrB_IndexUnaryOp;
 
 /* ------------------------------------------------------------------ context
  * graphblas/__init__.py:143,158-173 initialize(blocking=...), is_initialized() */
@@ -196,6 +198,83 @@ GRB_CUDA_DECLARE_TYPED(UINT64, uint64_t)
 GRB_CUDA_DECLARE_TYPED(FP32, float)
 GRB_CUDA_DECLARE_TYPED(FP64, double)
 extern const GrB_Index *GrB_ALL;
+
+/* ------------------------------------------------------------------ GrB_Scalar objects
+ * graphblas/core/scalar.py:83 (GrB_Scalar_new), :235-246 (nvals), :262-280 (clear / setElement_<T>), :199-216
+ * (extractElement_<T>); SURVEY.md section 8b lists them among the required lifecycle exports.  A scalar holds one value of
+ * a builtin type, or nothing (extractElement then returns GrB_NO_VALUE). */
+GrB_Info GrB_Scalar_new(GrB_Scalar *s, GrB_Type type);
+GrB_Info GrB_Scalar_free(GrB_Scalar *s);
+GrB_Info GrB_Scalar_dup(GrB_Scalar *t, const GrB_Scalar s);
+GrB_Info GrB_Scalar_clear(GrB_Scalar s);
+GrB_Info GrB_Scalar_nvals(GrB_Index *nvals, const GrB_Scalar s);
+GrB_Info GrB_Scalar_wait(GrB_Scalar s, GrB_WaitMode mode);
+GrB_Info GrB_Scalar_error(const char **error, const GrB_Scalar s);
+/* reduce to a GrB_Scalar: what the reference's default v.reduce() / A.reduce_scalar() call
+ * (graphblas/core/vector.py:1670, core/matrix.py:2750); an empty input leaves an empty scalar */
+GrB_Info GrB_Vector_reduce_Monoid_Scalar(GrB_Scalar s, const GrB_BinaryOp accum, const GrB_Monoid op, const GrB_Vector u,
+                                         const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_reduce_Monoid_Scalar(GrB_Scalar s, const GrB_BinaryOp accum, const GrB_Monoid op, const GrB_Matrix A,
+                                         const GrB_Descriptor desc);
+/* bind-1st / bind-2nd apply with a GrB_Scalar (graphblas/core/vector.py:1479, 1525; core/matrix.py:2474, 2520) */
+GrB_Info GrB_Vector_apply_BinaryOp1st_Scalar(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                             const GrB_Scalar x, const GrB_Vector u, const GrB_Descriptor desc);
+GrB_Info GrB_Vector_apply_BinaryOp2nd_Scalar(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                             const GrB_Vector u, const GrB_Scalar y, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_apply_BinaryOp1st_Scalar(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                             const GrB_Scalar x, const GrB_Matrix A, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_apply_BinaryOp2nd_Scalar(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                                             const GrB_Matrix A, const GrB_Scalar y, const GrB_Descriptor desc);
+/* select with a builtin GrB_IndexUnaryOp (GrB_TRIL, GrB_TRIU, GrB_DIAG, GrB_OFFDIAG, GrB_COLLE, GrB_COLGT, GrB_ROWLE, GrB_ROWGT,
+ * GrB_VALUE{EQ,NE,GT,GE,LT,LE}_<T>): graphblas/core/vector.py:1622-1624, core/matrix.py:2621-2623 */
+GrB_Info GrB_Vector_select_Scalar(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                  const GrB_Vector u, const GrB_Scalar y, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_select_Scalar(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                  const GrB_Matrix A, const GrB_Scalar y, const GrB_Descriptor desc);
+/* type-generic cores of the typed select names below: thunk passed by pointer + type */
+GrB_Info GrB_cuda_Vector_select(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                const GrB_Vector u, const void *thunk, GrB_Type thunk_type, const GrB_Descriptor desc);
+GrB_Info GrB_cuda_Matrix_select(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                const GrB_Matrix A, const void *thunk, GrB_Type thunk_type, const GrB_Descriptor desc);
+/* w<mask> accum= u and C<Mask> accum= A over all indices (GrB_ALL): graphblas/core/vector.py:1928, core/matrix.py:3300 */
+GrB_Info GrB_Vector_assign(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Vector u,
+                           const GrB_Index *indices, GrB_Index ni, const GrB_Descriptor desc);
+GrB_Info GrB_Vector_assign_Scalar(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Scalar s,
+                                  const GrB_Index *indices, GrB_Index ni, const GrB_Descriptor desc);
+GrB_Info GrB_Matrix_assign(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Matrix A,
+                           const GrB_Index *rows, GrB_Index nrows, const GrB_Index *cols, GrB_Index ncols, const GrB_Descriptor desc);
+/* the typed names of the above, one set per builtin type: f"GrB_Scalar_setElement_{T}" (core/scalar.py:272),
+ * f"GrB_Vector_apply_BinaryOp1st_{T}" (core/vector.py:1477), f"GrB_Matrix_reduce_{T}" (core/matrix.py:2754),
+ * f"GrB_Vector_select_{T}" (core/vector.py:1622) ... */
+#define GRB_CUDA_DECLARE_TYPED2(SFX, CT)                                                                                     \
+    GrB_Info GrB_Scalar_setElement_##SFX(GrB_Scalar s, CT x);                                                                \
+    GrB_Info GrB_Scalar_extractElement_##SFX(CT *x, const GrB_Scalar s);                                                     \
+    GrB_Info GrB_Matrix_setElement_##SFX(GrB_Matrix C, CT x, GrB_Index i, GrB_Index j);                                      \
+    GrB_Info GrB_Matrix_reduce_##SFX(CT *val, const GrB_BinaryOp accum, const GrB_Monoid op, const GrB_Matrix A,              \
+                                     const GrB_Descriptor desc);                                                             \
+    GrB_Info GrB_Vector_apply_BinaryOp1st_##SFX(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum,               \
+                                                const GrB_BinaryOp op, CT x, const GrB_Vector u, const GrB_Descriptor desc);  \
+    GrB_Info GrB_Vector_apply_BinaryOp2nd_##SFX(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum,               \
+                                                const GrB_BinaryOp op, const GrB_Vector u, CT y, const GrB_Descriptor desc);  \
+    GrB_Info GrB_Matrix_apply_BinaryOp1st_##SFX(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum,               \
+                                                const GrB_BinaryOp op, CT x, const GrB_Matrix A, const GrB_Descriptor desc);  \
+    GrB_Info GrB_Matrix_apply_BinaryOp2nd_##SFX(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum,               \
+                                                const GrB_BinaryOp op, const GrB_Matrix A, CT y, const GrB_Descriptor desc);  \
+    GrB_Info GrB_Vector_select_##SFX(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op, \
+                                     const GrB_Vector u, CT y, const GrB_Descriptor desc);                                   \
+    GrB_Info GrB_Matrix_select_##SFX(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op, \
+                                     const GrB_Matrix A, CT y, const GrB_Descriptor desc);
+GRB_CUDA_DECLARE_TYPED2(BOOL, bool)
+GRB_CUDA_DECLARE_TYPED2(INT8, int8_t)
+GRB_CUDA_DECLARE_TYPED2(INT16, int16_t)
+GRB_CUDA_DECLARE_TYPED2(INT32, int32_t)
+GRB_CUDA_DECLARE_TYPED2(INT64, int64_t)
+GRB_CUDA_DECLARE_TYPED2(UINT8, uint8_t)
+GRB_CUDA_DECLARE_TYPED2(UINT16, uint16_t)
+GRB_CUDA_DECLARE_TYPED2(UINT32, uint32_t)
+GRB_CUDA_DECLARE_TYPED2(UINT64, uint64_t)
+GRB_CUDA_DECLARE_TYPED2(FP32, float)
+GRB_CUDA_DECLARE_TYPED2(FP64, double)
 /* w<mask> accum= op(scalar, u) (scalar_first != 0) or op(u, scalar): GrB_Vector_apply_BinaryOp1st/2nd_<T> */
 GrB_Info GrB_cuda_Vector_apply_binop(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
                                      const GrB_Vector u, const void *scalar, GrB_Type scalar_type, int scalar_first,

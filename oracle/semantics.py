@@ -377,3 +377,35 @@ def reduce_scalar(monoid, A):
         for k in keys[1:]:
             acc = cast(f(acc, A.e[k]), A.dtype)
     return acc
+
+
+SELECT = {   # GrB_IndexUnaryOp predicates f(x, i, j, thunk): GraphBLAS C API 2.0 table 3.9; reference core/operator/select.py
+    "tril": lambda x, i, j, y: j <= i + y, "triu": lambda x, i, j, y: j >= i + y,
+    "diag": lambda x, i, j, y: j == i + y, "offdiag": lambda x, i, j, y: j != i + y,
+    "colle": lambda x, i, j, y: j <= y, "colgt": lambda x, i, j, y: j > y,
+    "rowle": lambda x, i, j, y: i <= y, "rowgt": lambda x, i, j, y: i > y,
+    "valueeq": lambda x, i, j, y: x == y, "valuene": lambda x, i, j, y: x != y,
+    "valuegt": lambda x, i, j, y: x > y, "valuege": lambda x, i, j, y: x >= y,
+    "valuelt": lambda x, i, j, y: x < y, "valuele": lambda x, i, j, y: x <= y,
+}
+_POSITIONAL = {"tril", "triu", "diag", "offdiag", "colle", "colgt", "rowle", "rowgt"}
+
+
+def select(C, M, accum, op, A, thunk, *, t0=False, complement=False, structure=False, replace=False):
+    """GrB_{Matrix,Vector}_select -- reference core/matrix.py:2560-2630, core/vector.py:1560-1631: keep the entries of A for which
+    op(value, row, col, thunk) holds; kept values are unchanged.  Value comparisons run in unify(A.dtype, thunk dtype); a vector is
+    an n x 1 SpMat here (col = 0)."""
+    A1 = A.T() if t0 else A
+    if (C.nrows, C.ncols) != (A1.nrows, A1.ncols):
+        raise ValueError("GrB_DIMENSION_MISMATCH")
+    f = SELECT[op]
+    if op in _POSITIONAL:
+        y = int(thunk)
+        T = {k: v for k, v in A1.e.items() if f(v, k[0], k[1], y)}
+    else:
+        tdt = np.bool_ if isinstance(thunk, bool) else np.int64 if isinstance(thunk, int) else np.float64 if isinstance(thunk, float) \
+            else np.asarray(thunk).dtype
+        D = unify(A.dtype, tdt)
+        y = cast(thunk, D)
+        T = {k: v for k, v in A1.e.items() if f(cast(v, D), k[0], k[1], y)}
+    return _write_back(C, T, A.dtype, None if M is None else M.dup(), accum, complement, structure, replace)

@@ -81,6 +81,16 @@ for a, acode in BADDS.items():
         name = GRB_BSR.get((a, m), f"GxB_{a}_{m}_BOOL")
         emit("GrB_Semiring", name, f'{{{acode}, OP_{m}, TC_BOOL, "{name}"}}')
 
+# ---- index-unary ops for select (reference graphblas/core/operator/indexunary.py, select.py: regex over dir(lib))
+for op in ["TRIL", "TRIU", "DIAG", "OFFDIAG", "COLLE", "COLGT", "ROWLE", "ROWGT"]:
+    emit("GrB_IndexUnaryOp", f"GrB_{op}", f'{{IOP_{op}, -1, "GrB_{op}"}}')
+for t in TYPES:
+    for op in ["VALUEEQ", "VALUENE", "VALUEGT", "VALUEGE", "VALUELT", "VALUELE"]:
+        emit("GrB_IndexUnaryOp", f"GrB_{op}_{t}", f'{{IOP_{op}, TC_{t}, "GrB_{op}_{t}"}}')
+for t in ["INT32", "INT64"]:
+    for op in ["ROWINDEX", "COLINDEX", "DIAGINDEX"]:
+        emit("GrB_IndexUnaryOp", f"GrB_{op}_{t}", f'{{IOP_{op}, -1, "GrB_{op}_{t}"}}')
+
 # ---- descriptors  (reference graphblas/core/descriptor.py:51-84)
 for r in (0, 1):
     for s in (0, 1):

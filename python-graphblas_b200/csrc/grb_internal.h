@@ -20,6 +20,11 @@ enum OpCode : int {
     OP_ISNE, OP_COUNT
 };
 enum UnaryCode : int { UOP_IDENTITY = 1, UOP_AINV, UOP_MINV, UOP_LNOT, UOP_ABS, UOP_ONE, UOP_BNOT };
+// GrB_IndexUnaryOp codes (select): positional ones take an int64 thunk, VALUE* compare the entry with a thunk of the op's type
+enum IndexOpCode : int {
+    IOP_TRIL = 1, IOP_TRIU, IOP_DIAG, IOP_OFFDIAG, IOP_COLLE, IOP_COLGT, IOP_ROWLE, IOP_ROWGT, IOP_VALUEEQ, IOP_VALUENE,
+    IOP_VALUEGT, IOP_VALUEGE, IOP_VALUELT, IOP_VALUELE, IOP_ROWINDEX, IOP_COLINDEX, IOP_DIAGINDEX
+};
 
 static inline size_t type_size(int tc) {
     static const size_t s[TC_COUNT] = {1, 1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
@@ -32,10 +37,12 @@ struct GrB_UnaryOp_opaque { int opcode; int type; const char *name; };
 struct GrB_BinaryOp_opaque { int opcode; int type; int ztype; const char *name; };
 struct GrB_Monoid_opaque { int opcode; int type; const char *name; };
 struct GrB_Semiring_opaque { int add; int mul; int type; const char *name; };
+struct GrB_IndexUnaryOp_opaque { int opcode; int type; const char *name; };   // type: TC_* of VALUE* ops, -1 for positional ones
 struct GrB_Descriptor_opaque { bool replace, comp, structure, t0, t1; const char *name; };
 
 #define GRB_MAGIC_MATRIX 0x4d61747269784742ull
 #define GRB_MAGIC_VECTOR 0x566563746f724742ull
+#define GRB_MAGIC_SCALAR 0x5363616c61724742ull
 #define GRB_MAGIC_FREED 0x4672656564474221ull
 
 struct CsrArrays {
@@ -85,6 +92,18 @@ struct GrB_Vector_opaque {
     int64_t nvals;        // -1 = unknown (count lazily)
     std::string err;
 };
+
+// a GrB_Scalar lives on the host: one value of a builtin type, or empty
+struct GrB_Scalar_opaque {
+    uint64_t magic;
+    int type;
+    bool has;
+    unsigned char buf[8];
+    std::string err;
+};
+static inline bool valid(const GrB_Scalar s) { return s && s->magic == GRB_MAGIC_SCALAR; }
+// host-side cast between builtin types (C semantics; anything -> BOOL is "!= 0")
+void host_cast(void *dst, int dst_type, const void *src, int src_type);
 
 // ------------------------------------------------------------------ runtime services (runtime.cu)
 extern cudaStream_t g_stream;

@@ -479,9 +479,11 @@ extern "C" GrB_Info GrB_cuda_Vector_build(GrB_Vector w, const GrB_Index *I, cons
     GRB_TRY(vector_count(w));
     if (w->nvals != 0) return set_error(&w->err, GrB_OUTPUT_NOT_EMPTY, "build: output already has entries");
     if (nvals == 0) return GrB_SUCCESS;
-    // bounds are checked before the dense arrays are created (a 2^59-sized vector must fail cleanly)
-    for (GrB_Index k = 0; k < nvals; k++)
-        if (I[k] >= (GrB_Index)w->n) return set_error(&w->err, GrB_INDEX_OUT_OF_BOUNDS, "build: index %llu out of bounds", (unsigned long long)I[k]);
+    // a vector too long for the dense layout (2^59 + 1 in the reference's tests) must fail cleanly: bad indices first, then the
+    // size; for every other vector the bounds check is done on the device while the sort keys are made
+    if ((uint64_t)w->n > (uint64_t)INT32_MAX)
+        for (GrB_Index k = 0; k < nvals; k++)
+            if (I[k] >= (GrB_Index)w->n) return set_error(&w->err, GrB_INDEX_OUT_OF_BOUNDS, "build: index %llu out of bounds", (unsigned long long)I[k]);
     GRB_TRY(vector_ensure_arrays(w));
     BuildResult r;
     GRB_TRY(build_sorted_unique(&r, I, nullptr, X, xtype->code, w->type, (int64_t)nvals, (uint64_t)w->n, 1, dup, &w->err));

@@ -246,9 +246,9 @@ void vector_release(GrB_Vector v) {
 
 GrB_Info vector_ensure_arrays(GrB_Vector v) {
     if (v->vals && v->present) return GrB_SUCCESS;
-    if (v->n > ((int64_t)1 << 36))
+    if (v->n > (int64_t)INT32_MAX)   // positions are 32-bit on the build / scatter / frontier paths
         return set_error(&v->err, GrB_OUT_OF_MEMORY,
-                         "vector of size %lld cannot be held in the dense device layout", (long long)v->n);
+                         "vector of size %lld cannot be held in the dense device layout (at most 2^31 - 1 positions)", (long long)v->n);
     size_t n = (size_t)(v->n > 0 ? v->n : 1);
     v->vals = dev_alloc(n * type_size(v->type));
     v->present = (uint8_t *)dev_alloc(n);

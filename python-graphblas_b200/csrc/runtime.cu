@@ -149,7 +149,7 @@ static void cache_flush() {
 }
 
 void *dev_alloc(size_t bytes) {
-    if (bytes == 0) bytes = 16;
+    bytes += 64;   // slack: TMA bulk copies read 16-byte granules that may run a few elements past an array's logical end (spgemm_tile.cuh)
     void *p = nullptr;
     if (bytes >= CACHE_MIN_BYTES) {
         std::lock_guard<std::mutex> lk(g_mu);

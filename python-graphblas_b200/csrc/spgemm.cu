@@ -240,7 +240,7 @@ static BinSpec make_bin_spec(size_t entry_bytes) {
         if (s.maxcount[b] < s.maxcount[b - 1]) s.maxcount[b] = s.maxcount[b - 1];   // a tighter factor must not reorder the bins
     }
     s.maxcount[NBINS - 1] = INT64_MAX;
-    s.flags = (opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0) | (opt_get_int("spgemm_elect", 0) != 0 ? 2 : 0);
+    s.flags = opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0;
     return s;
 }
 __device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
@@ -488,504 +488,6 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
     }
 }
 
-// ------------------------------------------------------------------ numeric kernels without shared-memory atomics
-// A shared-memory atomic costs ~2 SM cycles per lane on sm_100 (64 cycles per warp instruction, whatever the addresses), which
-// made the atomicCAS of the hash insert the limiter of the numeric phase: products arrive faster than one CAS per product
-// can retire.  Most products of a sparse product open a NEW slot (nnz(C) ~ flops), so the claim is done with plain loads and
-// stores instead, in rounds of one product per thread separated by warp / CTA barriers:
-//   probe   every thread walks its probe sequence on the table as it stood at the barrier (nobody writes keys now): a slot
-//           with its key -> combine into the (final) value and done; the first EMPTY slot -> candidate;
-//   elect   candidates store a tag -(thread id + 2) into the KEY word of their slot -- exactly one tag survives;
-//   own     the thread that reads back its own tag owns the slot: it stores the value, then the real key (tags are < -1,
-//           keys are >= 0, so a slower candidate reading the word meanwhile can never mistake either for its own tag);
-//   settle  the others re-read the key: same key -> atomic combine (rare), other key -> probe on from the next slot next round.
-// Threads holding the same key compute the same candidate from the same snapshot, so a key can never occupy two slots;
-// every tag is replaced by its winner's key before the next probe phase, so probes only ever see EMPTY or real keys.
-__device__ __forceinline__ void elect_store(int *slot, int tag) { *reinterpret_cast<volatile int *>(slot) = tag; }
-__device__ __forceinline__ int elect_load(const int *slot) { return *reinterpret_cast<const volatile int *>(slot); }
-
-template <typename T> static __host__ __device__ inline size_t warp_elect_bytes(int cap) {
-    // s_bs[32] (8 B) | vals[cap] | s_av[32] | keys[cap] | s_off[36]
-    return ((size_t)32 * 8 + (size_t)(cap + 32) * sizeof(T) + (size_t)(cap + 36) * 4 + 15) & ~(size_t)15;
-}
-
-template <typename SR, typename T>
-__global__ void __launch_bounds__(128)
-spgemm_warp_elect_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
-                         const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
-                         const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
-                         int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (g >= n_rows) return;   // warps are independent: no CTA-wide barrier in this kernel
-    unsigned char *base = s_raw + warp_elect_bytes<T>(cap) * wib;
-    int64_t *s_bs = reinterpret_cast<int64_t *>(base);
-    T *vals = reinterpret_cast<T *>(s_bs + 32);
-    T *s_av = vals + cap;
-    int *keys = reinterpret_cast<int *>(s_av + 32);
-    int *s_off = keys + cap;
-    const int64_t row = rows[g];
-    const unsigned tsize = (unsigned)table_size_for(cnt[row], cap, tf8);
-    for (unsigned t = lane; t < tsize; t += 32) keys[t] = HASH_EMPTY;
-    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
-    for (int64_t c0 = a_beg; c0 < a_end; c0 += 32) {
-        __syncwarp();   // table init / the previous chunk's readers of s_*
-        int len = 0;
-        if (c0 + lane < a_end) {
-            const int64_t k = c0 + lane;
-            const int32_t br = Aj[k];
-            const int64_t bs = Bp[br];
-            len = (int)(Bp[br + 1] - bs);
-            s_bs[lane] = bs;
-            if (sr.reads_a()) s_av[lane] = Ax[k];
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += up;
-        }
-        s_off[lane] = incl - len;
-        if (lane == 31) s_off[32] = incl;
-        __syncwarp();
-        const int P = s_off[32];
-        int lo = 0;   // products of a lane only move forward, so the owning A entry is found by walking, never by searching
-        for (int base0 = 0; base0 < P; base0 += 32 * UNROLL) {
-            int jj[UNROLL];
-            T bb[UNROLL], aa[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const int pp = base0 + u * 32 + lane;
-                jj[u] = HASH_EMPTY;
-                if (pp < P) {
-                    while (s_off[lo + 1] <= pp) lo++;
-                    const int64_t q = s_bs[lo] + (pp - s_off[lo]);
-                    jj[u] = Bj[q];
-                    if (sr.reads_b()) bb[u] = Bx[q];
-                    if (sr.reads_a()) aa[u] = s_av[lo];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                if (base0 + u * 32 >= P) break;   // uniform
-                const int j = jj[u];
-                bool have = j != HASH_EMPTY;
-                const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                unsigned h = have ? hash_slot(j, tsize) : 0u;
-                while (true) {
-                    bool claim = false;
-                    if (have) {
-                        int k = keys[h];
-                        while (k != HASH_EMPTY && k != j) {
-                            h = (h + 1 == tsize) ? 0 : h + 1;
-                            k = keys[h];
-                        }
-                        if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                        else claim = true;
-                    }
-                    if (!__any_sync(FULL, claim)) break;
-                    __syncwarp();   // every probe of this round has read its keys
-                    if (claim) elect_store(&keys[h], -(lane + 2));
-                    __syncwarp();
-                    if (claim && elect_load(&keys[h]) == -(lane + 2)) {
-                        vals[h] = pr;
-                        elect_store(&keys[h], j);
-                        have = false;
-                        claim = false;
-                    }
-                    __syncwarp();
-                    if (claim) {   // lost the slot: to the same key (combine) or to another one (probe on next round)
-                        if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                        else h = (h + 1 == tsize) ? 0 : h + 1;
-                    }
-                }
-            }
-        }
-    }
-    __syncwarp();
-    // drain: ballot compaction, no atomics
-    const int64_t ob = Op[row];
-    int outpos = 0;
-    for (unsigned t0 = 0; t0 < tsize; t0 += 32) {
-        const unsigned t = t0 + lane;
-        const int key = t < tsize ? keys[t] : HASH_EMPTY;
-        const unsigned m = __ballot_sync(FULL, key >= 0);
-        if (key >= 0) {
-            const int pos = outpos + __popc(m & ((1u << lane) - 1u));
-            Oj[ob + pos] = key;
-            Ox[ob + pos] = vals[t];
-        }
-        outpos += __popc(m);
-    }
-    if (lane == 0 && row_nnz) row_nnz[row] = outpos;
-}
-
-static inline size_t block_elect_bytes(int cap, int threads, size_t val_bytes) {
-    return (((size_t)cap * (val_bytes + 4) + 15) & ~(size_t)15) + block_stage_bytes(threads, val_bytes);
-}
-
-template <typename SR, typename T>
-__global__ void spgemm_block_elect_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, const int64_t *__restrict__ cnt,
-                                          const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
-                                          const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
-                                          int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
-                                          T *__restrict__ Ox) {
-    // dynamic shared memory: vals[cap] | keys[cap] | s_bs[nthreads] | s_off[nthreads + 1 ..] | s_av[nthreads]
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_wsum[MAX_THREADS / 32];
-    __shared__ int s_count;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    T *vals = reinterpret_cast<T *>(s_raw);
-    int *keys = reinterpret_cast<int *>(vals + cap);
-    int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + ((((size_t)cap * (sizeof(T) + 4)) + 15) & ~(size_t)15));
-    int *s_off = reinterpret_cast<int *>(s_bs + nthreads);
-    T *s_av = reinterpret_cast<T *>(s_off + ((nthreads + 4) & ~3));
-    const int64_t row = rows[blockIdx.x];
-    const unsigned tsize = (unsigned)table_size_for(cnt[row], cap, tf8);
-    for (unsigned t = tid; t < tsize; t += nthreads) keys[t] = HASH_EMPTY;
-    if (tid == 0) s_count = 0;
-
-    const int wlane = tid & 31, warp = tid >> 5;
-    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
-    for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
-        const int chunk_n = (int)((a_end - c0 < nthreads) ? (a_end - c0) : nthreads);
-        int len = 0;
-        if (tid < chunk_n) {
-            const int64_t k = c0 + tid;
-            const int32_t br = Aj[k];
-            const int64_t bs = Bp[br];
-            len = (int)(Bp[br + 1] - bs);
-            s_bs[tid] = bs;
-            if (sr.reads_a()) s_av[tid] = Ax[k];
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (wlane >= o) incl += up;
-        }
-        if (wlane == 31) s_wsum[warp] = incl;
-        __syncthreads();   // also orders the table init / the previous chunk's rounds before this chunk's
-        int base = 0;
-        for (int w = 0; w < warp; w++) base += s_wsum[w];
-        s_off[tid] = base + incl - len;
-        if (tid == nthreads - 1) s_off[nthreads] = base + incl;
-        __syncthreads();
-        const int P = s_off[nthreads];
-        for (int base0 = 0; base0 < P; base0 += nthreads * UNROLL) {   // trip counts are uniform over the CTA (barriers inside)
-            int jj[UNROLL];
-            T bb[UNROLL], aa[UNROLL];
-            int pp = base0 + warp * (32 * UNROLL) + wlane;
-            int lo = 0;
-            if (pp < P) {
-                int hi = chunk_n - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_off[mid] <= pp) lo = mid;
-                    else hi = mid - 1;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                jj[u] = HASH_EMPTY;
-                if (pp < P) {
-                    while (s_off[lo + 1] <= pp) lo++;
-                    const int64_t q = s_bs[lo] + (pp - s_off[lo]);
-                    jj[u] = Bj[q];
-                    if (sr.reads_b()) bb[u] = Bx[q];
-                    if (sr.reads_a()) aa[u] = s_av[lo];
-                }
-                pp += 32;
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                if (base0 + u * 32 >= P) break;   // uniform: no thread of the CTA has a product in this slot
-                const int j = jj[u];
-                bool have = j != HASH_EMPTY;
-                const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                unsigned h = have ? hash_slot(j, tsize) : 0u;
-                while (true) {
-                    bool claim = false;
-                    if (have) {
-                        int k = keys[h];
-                        while (k != HASH_EMPTY && k != j) {
-                            h = (h + 1 == tsize) ? 0 : h + 1;
-                            k = keys[h];
-                        }
-                        if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                        else claim = true;
-                    }
-                    if (!__syncthreads_or(claim)) break;   // barrier: every probe of this round has read its keys
-                    if (claim) elect_store(&keys[h], -(tid + 2));
-                    __syncthreads();
-                    if (claim && elect_load(&keys[h]) == -(tid + 2)) {
-                        vals[h] = pr;
-                        elect_store(&keys[h], j);
-                        have = false;
-                        claim = false;
-                    }
-                    __syncthreads();
-                    if (claim) {
-                        if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                        else h = (h + 1 == tsize) ? 0 : h + 1;
-                    }
-                }
-            }
-        }
-        __syncthreads();   // s_* arrays are rewritten by the next chunk
-    }
-    __syncthreads();
-    const int64_t ob = Op[row];
-    for (unsigned t = tid; t < tsize; t += nthreads) {
-        const int key = keys[t];
-        if (key >= 0) {
-            const int pos = atomicAdd(&s_count, 1);   // warp-aggregated by the compiler
-            Oj[ob + pos] = key;
-            Ox[ob + pos] = vals[t];
-        }
-    }
-    if (row_nnz) {
-        __syncthreads();
-        if (tid == 0) row_nnz[row] = s_count;
-    }
-}
-
-// ------------------------------------------------------------------ grouped small rows (numeric, one-pass, unmasked)
-// A row of a sparse product has only a few hundred products, so a CTA per row spends most of its instructions on fixed
-// per-row work (table init, staging, drain, barriers) and most of its time waiting on the dependent load chain of that one
-// row.  Here a 256-thread CTA takes a GROUP of consecutive rows -- all rows with <= R products whose staging offsets fall in
-// one window of the flops prefix, < G products in total -- gives every row its own slice of one shared-memory table, and
-// walks the products of the WHOLE group as one flat index space: every thread always has work, the A entries of the group
-// are one contiguous, coalesced read, and the owner-election rounds (see above) are full.  Rows with more than R products
-// keep the CTA-per-row kernels.
-constexpr int GROUP_THREADS = 256;
-constexpr int GROUP_RMAX = 256;   // rows per batch == threads, so the per-row scan is one pass
-__host__ __device__ __forceinline__ int group_tsize(int64_t c, int tf8) { return (int)((c * tf8) >> 3) + 2; }
-
-struct SmallRowPred {
-    const int64_t *flops; int64_t R;
-    __device__ __forceinline__ bool operator()(const int &i) const { const int64_t f = flops[i]; return f > 0 && f <= R; }
-};
-// big[i] = flops of the rows the bins keep (the others are binned as empty); sf[q] = flops of the q-th small row
-__global__ void split_flops_kernel(int64_t nrows, const int64_t *__restrict__ flops, int64_t R, int64_t *__restrict__ big) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = (int64_t)gridDim.x * blockDim.x;
-    for (; i <= nrows; i += s) {
-        const int64_t f = i < nrows ? flops[i] : 0;
-        big[i] = f <= R ? 0 : f;
-    }
-}
-__global__ void gather_small_flops_kernel(int64_t n_small, const int32_t *__restrict__ small_rows, const int64_t *__restrict__ flops,
-                                          int64_t *__restrict__ sf) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = (int64_t)gridDim.x * blockDim.x;
-    for (; q <= n_small; q += s) sf[q] = q < n_small ? flops[small_rows[q]] : 0;
-}
-// g_start[k] = first position of the small-row list whose flops prefix is >= k * window; g_start[n_groups] = n_small
-__global__ void group_starts_kernel(int64_t n_small, const int64_t *__restrict__ F, int64_t window, int64_t n_groups,
-                                    int64_t *__restrict__ g_start) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > n_groups) return;
-    if (k == n_groups) { g_start[k] = n_small; return; }
-    const int64_t target = k * window;
-    int64_t lo = 0, hi = n_small;   // first q in [0, n_small] with F[q] >= target
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (F[mid] >= target) hi = mid;
-        else lo = mid + 1;
-    }
-    g_start[k] = lo;
-}
-
-static inline size_t group_smem_bytes(int tslots, size_t val_bytes) {
-    size_t b = (((size_t)tslots * (val_bytes + 4)) + 15) & ~(size_t)15;                       // vals | keys
-    b += (size_t)GROUP_THREADS * 8;                                                          // s_bs
-    b += (size_t)(GROUP_THREADS + 4) * 4;                                                    // s_off
-    b += (size_t)GROUP_THREADS * 4 * 2;                                                      // s_tb, s_ts
-    b += (size_t)(GROUP_RMAX + 4) * 4 * 2;                                                   // s_tbase, s_aoff
-    b += (size_t)GROUP_RMAX * 8;                                                             // s_abeg
-    b += (((size_t)GROUP_THREADS * val_bytes) + 15) & ~(size_t)15;                           // s_av
-    return b;
-}
-
-template <typename SR, typename T>
-__global__ void __launch_bounds__(GROUP_THREADS)
-spgemm_group_elect_kernel(SR sr, const int64_t *__restrict__ g_start, const int32_t *__restrict__ small_rows, int tf8, int tslots,
-                          const int64_t *__restrict__ flops, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj,
-                          const T *__restrict__ Ax, const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj,
-                          const T *__restrict__ Bx, int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op,
-                          int32_t *__restrict__ Oj, T *__restrict__ Ox) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_wsum[GROUP_THREADS / 32], s_wsum2[GROUP_THREADS / 32];
-    constexpr int NT = GROUP_THREADS;
-    const int tid = threadIdx.x, wlane = tid & 31, warp = tid >> 5;
-    T *vals = reinterpret_cast<T *>(s_raw);
-    int *keys = reinterpret_cast<int *>(vals + tslots);
-    unsigned char *q = s_raw + ((((size_t)tslots * (sizeof(T) + 4)) + 15) & ~(size_t)15);
-    int64_t *s_bs = reinterpret_cast<int64_t *>(q); q += (size_t)NT * 8;
-    int *s_off = reinterpret_cast<int *>(q); q += (size_t)(NT + 4) * 4;
-    int *s_tb = reinterpret_cast<int *>(q); q += (size_t)NT * 4;
-    int *s_ts = reinterpret_cast<int *>(q); q += (size_t)NT * 4;
-    int *s_tbase = reinterpret_cast<int *>(q); q += (size_t)(GROUP_RMAX + 4) * 4;
-    int *s_aoff = reinterpret_cast<int *>(q); q += (size_t)(GROUP_RMAX + 4) * 4;
-    int64_t *s_abeg = reinterpret_cast<int64_t *>(q); q += (size_t)GROUP_RMAX * 8;
-    T *s_av = reinterpret_cast<T *>(q);
-
-    const int64_t gr0 = g_start[blockIdx.x], gr1 = g_start[blockIdx.x + 1];
-    for (int64_t rb = gr0; rb < gr1; rb += GROUP_RMAX) {
-        const int nr = (int)((gr1 - rb < GROUP_RMAX) ? (gr1 - rb) : GROUP_RMAX);
-        __syncthreads();   // the previous batch's drain is done with the table and the row arrays
-        // ---- per-row slices of the table and the (batch-local) prefix of the rows' A-entry counts; rb indexes the small-row list
-        int ts = 0, deg = 0;
-        if (tid < nr) {
-            const int64_t row = small_rows[rb + tid];
-            ts = group_tsize(flops[row], tf8);
-            const int64_t ab = Ap[row];
-            deg = (int)(Ap[row + 1] - ab);
-            s_abeg[tid] = ab;
-        }
-        int incl = ts, dincl = deg;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o), dup = __shfl_up_sync(0xffffffffu, dincl, o);
-            if (wlane >= o) { incl += up; dincl += dup; }
-        }
-        if (wlane == 31) { s_wsum[warp] = incl; s_wsum2[warp] = dincl; }
-        __syncthreads();
-        int wbase = 0, dbase = 0;
-        for (int w = 0; w < warp; w++) { wbase += s_wsum[w]; dbase += s_wsum2[w]; }
-        if (tid < nr) { s_tbase[tid] = wbase + incl - ts; s_aoff[tid] = dbase + dincl - deg; }
-        if (tid == nr - 1) { s_tbase[nr] = wbase + incl; s_aoff[nr] = dbase + dincl; }
-        __syncthreads();
-        const int total_slots = s_tbase[nr];   // <= tslots by construction of the groups
-        for (int t = tid; t < total_slots; t += NT) keys[t] = HASH_EMPTY;
-        const int a_total = s_aoff[nr];
-        // ---- the A entries of the batch, a chunk of NT at a time
-        for (int c0 = 0; c0 < a_total; c0 += NT) {
-            const int chunk_n = (a_total - c0 < NT) ? (a_total - c0) : NT;
-            int len = 0;
-            if (tid < chunk_n) {
-                const int k = c0 + tid;
-                int lo = 0, hi = nr - 1;   // owning row: the last r with s_aoff[r] <= k (rows without entries are skipped)
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_aoff[mid] <= k) lo = mid;
-                    else hi = mid - 1;
-                }
-                const int tb = s_tbase[lo];
-                s_tb[tid] = tb;
-                s_ts[tid] = s_tbase[lo + 1] - tb;
-                const int64_t ak = s_abeg[lo] + (k - s_aoff[lo]);
-                const int32_t br = Aj[ak];
-                const int64_t bs = Bp[br];
-                len = (int)(Bp[br + 1] - bs);
-                s_bs[tid] = bs;
-                if (sr.reads_a()) s_av[tid] = Ax[ak];
-            }
-            int pin = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, pin, o);
-                if (wlane >= o) pin += up;
-            }
-            __syncthreads();   // s_wsum free again; also orders the key init / the previous chunk's rounds before this chunk's
-            if (wlane == 31) s_wsum[warp] = pin;
-            __syncthreads();
-            int pbase = 0;
-            for (int w = 0; w < warp; w++) pbase += s_wsum[w];
-            s_off[tid] = pbase + pin - len;
-            if (tid == NT - 1) s_off[NT] = pbase + pin;
-            __syncthreads();
-            const int P = s_off[NT];
-            for (int base0 = 0; base0 < P; base0 += NT * UNROLL) {   // uniform trip counts: barriers inside
-                int jj[UNROLL], hb[UNROLL], hs[UNROLL];
-                T bb[UNROLL], aa[UNROLL];
-                int pp = base0 + warp * (32 * UNROLL) + wlane;
-                int lo = 0;
-                if (pp < P) {
-                    int hi = chunk_n - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (s_off[mid] <= pp) lo = mid;
-                        else hi = mid - 1;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    jj[u] = HASH_EMPTY;
-                    if (pp < P) {
-                        while (s_off[lo + 1] <= pp) lo++;
-                        const int64_t e = s_bs[lo] + (pp - s_off[lo]);
-                        jj[u] = Bj[e];
-                        if (sr.reads_b()) bb[u] = Bx[e];
-                        if (sr.reads_a()) aa[u] = s_av[lo];
-                        hb[u] = s_tb[lo];
-                        hs[u] = s_ts[lo];
-                    }
-                    pp += 32;
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    if (base0 + u * 32 >= P) break;   // uniform: no thread of the CTA has a product in this slot
-                    const int j = jj[u];
-                    bool have = j != HASH_EMPTY;
-                    const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                    const int tb = have ? hb[u] : 0, te = have ? hb[u] + hs[u] : 1;
-                    int h = have ? tb + (int)hash_slot(j, (unsigned)hs[u]) : 0;
-                    while (true) {
-                        bool claim = false;
-                        if (have) {
-                            int k = keys[h];
-                            while (k != HASH_EMPTY && k != j) {
-                                h = (h + 1 == te) ? tb : h + 1;
-                                k = keys[h];
-                            }
-                            if (k == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                            else claim = true;
-                        }
-                        if (!__syncthreads_or(claim)) break;   // barrier: every probe of this round has read its keys
-                        if (claim) elect_store(&keys[h], -(tid + 2));
-                        __syncthreads();
-                        if (claim && elect_load(&keys[h]) == -(tid + 2)) {
-                            vals[h] = pr;
-                            elect_store(&keys[h], j);
-                            have = false;
-                            claim = false;
-                        }
-                        __syncthreads();
-                        if (claim) {
-                            if (keys[h] == j) { atomic_combine(sr, &vals[h], pr); have = false; }
-                            else h = (h + 1 == te) ? tb : h + 1;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- drain: a warp per row, ballot compaction into the staging row
-        for (int r = warp; r < nr; r += NT / 32) {
-            const int tb = s_tbase[r], tsz = s_tbase[r + 1] - tb;
-            const int64_t row = small_rows[rb + r];
-            const int64_t ob = Op[row];
-            int outpos = 0;
-            for (int t0 = 0; t0 < tsz; t0 += 32) {
-                const int t = t0 + wlane;
-                const int key = t < tsz ? keys[tb + t] : HASH_EMPTY;
-                const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
-                if (key >= 0) {
-                    const int pos = outpos + __popc(m & ((1u << wlane) - 1u));
-                    Oj[ob + pos] = key;
-                    Ox[ob + pos] = vals[tb + t];
-                }
-                outpos += __popc(m);
-            }
-            if (wlane == 0) row_nnz[row] = outpos;
-        }
-    }
-}
-
 __global__ void gtable_sizes_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt,
                                     int64_t *__restrict__ sizes) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -997,17 +499,29 @@ __global__ void i64_copy_kernel(int64_t *dst, const int64_t *src, int64_t n) {
     const int64_t s = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += s) dst[i] = src[i];
 }
-__global__ void reduce_sum_max_kernel(const int64_t *__restrict__ v, int64_t n, unsigned long long *__restrict__ out) {
-    unsigned long long sum = 0, mx = 0;
+// out[0] = sum, out[1] = max, out[2] = sum of the values above R, out[3] = how many are above R
+__global__ void reduce_sum_max_kernel(const int64_t *__restrict__ v, int64_t n, int64_t R, unsigned long long *__restrict__ out) {
+    unsigned long long sum = 0, mx = 0, big = 0, nbig = 0;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t s = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += s) { unsigned long long x = (unsigned long long)v[i]; sum += x; mx = x > mx ? x : mx; }
+    for (; i < n; i += s) {
+        const unsigned long long x = (unsigned long long)v[i];
+        sum += x;
+        mx = x > mx ? x : mx;
+        if ((int64_t)x > R) { big += x; nbig++; }
+    }
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_down_sync(0xffffffffu, sum, o);
+        big += __shfl_down_sync(0xffffffffu, big, o);
+        nbig += __shfl_down_sync(0xffffffffu, nbig, o);
         unsigned long long om = __shfl_down_sync(0xffffffffu, mx, o);
         mx = om > mx ? om : mx;
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], sum);
+        atomicMax(&out[1], mx);
+        if (nbig) { atomicAdd(&out[2], big); atomicAdd(&out[3], nbig); }
+    }
 }
 // masked product: the table holds the mask row, the work is the row's flops; bin by whichever asks for the bigger CTA
 __global__ void masked_count_kernel(int64_t nrows, const int64_t *__restrict__ flops, const int64_t *__restrict__ Mp,
@@ -1057,6 +571,8 @@ compact_rows_kernel(int64_t nrows, const int64_t *__restrict__ Sp, const int64_t
     }
 }
 
+#include "spgemm_tile.cuh"
+
 // ------------------------------------------------------------------ host orchestration
 struct Bins {
     int32_t *rows = nullptr;           // row ids grouped by bin
@@ -1100,10 +616,6 @@ static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const i
     return GrB_SUCCESS;
 }
 
-struct GroupArgs {   // grouped small rows (spgemm_group_elect_kernel); n_groups == 0: not used
-    const int64_t *g_start = nullptr; const int32_t *small_rows = nullptr; int64_t n_groups = 0; int64_t R = 0; int tf8 = 12; int tslots = 0;
-    const int64_t *flops = nullptr;
-};
 struct HashArgs {
     const int64_t *Ap; const int32_t *Aj; const void *Ax;
     const int64_t *Bp; const int32_t *Bj; const void *Bx;
@@ -1145,31 +657,6 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
         if (n == 0) return GrB_SUCCESS;
         const int32_t *rows = bins.rows + bins.start[b];
         const int cap = bins.spec.cap[b], threads = bins.spec.threads[b];
-        if constexpr (NUMERIC && sizeof(T) >= 4) {
-            // atomics-free owner-election kernels (see above): unmasked numeric products with shared-memory tables
-            if (!a.mk.Mp && b < NBINS - 1 && (bins.spec.flags & 2) && b >= (int)opt_get_int("spgemm_elect_from_bin", 1) &&
-                b <= (int)opt_get_int("spgemm_elect_to_bin", NBINS)) {
-                const bool warp_rows = b <= 2 || (size_t)cap * (sizeof(T) + 4) <= (size_t)opt_get_int("spgemm_warp_table_bytes", 16384);
-                if (warp_rows) {
-                    const int rpb = 4;
-                    const size_t smem = warp_elect_bytes<T>(cap) * rpb;
-                    auto kern = spgemm_warp_elect_kernel<SR, T>;
-                    if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    LAUNCH_NOTE("spgemm_numeric_warp");
-                    kern<<<(unsigned)((n + rpb - 1) / rpb), 32 * rpb, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
-                } else {
-                    const size_t smem = block_elect_bytes(cap, threads, sizeof(T));
-                    auto kern = spgemm_block_elect_kernel<SR, T>;
-                    CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-                    LAUNCH_NOTE("spgemm_numeric_block");
-                    kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
-                }
-                cudaError_t le = cudaGetLastError();
-                if (le != cudaSuccess)
-                    return set_error(err, GrB_PANIC, "spgemm elect kernel launch failed in bin %d (cap %d, %d threads, %lld rows): %s", b, cap, threads, (long long)n, cudaGetErrorString(le));
-                return GrB_SUCCESS;
-            }
-        }
         if (b <= 2) {
             const int rpb = threads / 32;
             const size_t per = (((size_t)cap * entry + 8) + 15) & ~(size_t)15;
@@ -1274,8 +761,7 @@ template <typename T> static size_t numeric_entry_bytes() { return (Packed<T>::v
 // numeric pass writing row i at O*[Op[i]...]; row_nnz (optional) receives exact counts
 template <typename T>
 static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p, const Bins &bins, const int64_t *cnt,
-                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, MaskArgs mk, std::string *err,
-                                     const GroupArgs &ga = GroupArgs()) {
+                                     int64_t *row_nnz, const int64_t *Op, int32_t *Oj, void *Ox, MaskArgs mk, std::string *err) {
     GrB_Info info = GrB_SUCCESS;
     const int T_code = type_code_of<T>();
     GRB_DISPATCH_SEMIRING(op->add, op->mul, T, SRT, sr, {
@@ -1285,19 +771,6 @@ static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p,
         if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
         if (!info) {
             HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt, mk};
-            if constexpr (sizeof(T) >= 4) {
-                if (ga.n_groups > 0) {   // small rows first: many short CTAs, the big-row bins then fill the tail
-                    const size_t smem = group_smem_bytes(ga.tslots, sizeof(T));
-                    auto kern = spgemm_group_elect_kernel<SRT, T>;
-                    cudaError_t ge = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (ge == cudaSuccess) {
-                        LAUNCH_NOTE("spgemm_numeric_group");
-                        kern<<<(unsigned)ga.n_groups, GROUP_THREADS, smem, g_stream>>>(sr, ga.g_start, ga.small_rows, ga.tf8, ga.tslots, ga.flops, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
-                        ge = cudaGetLastError();
-                    }
-                    if (ge != cudaSuccess) info = cuda_fail(err, ge, "grouped spgemm kernel");
-                }
-            }
             if (!info) {
                 if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
                 else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
@@ -1314,6 +787,185 @@ static void launch_compact(int64_t m, const int64_t *Sp, const int64_t *Cp, cons
     int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)g_num_sms * 32);
     LAUNCH_NOTE("spgemm_compact");
     compact_rows_kernel<T><<<blocks, 256, 0, g_stream>>>(m, Sp, Cp, Sj, (const T *)Sx, Cj, (T *)Cx);
+}
+
+
+// ------------------------------------------------------------------ tiled one-pass (spgemm_tile.cuh): host side
+struct TileCfg { bool on = false; int threads = 256, ctas = 2, tcap = 0, scap = 0, tf8 = 12; int64_t R = 0, W = 0; size_t smem = 0; };
+struct TileScratch {
+    int64_t *small = nullptr, *big = nullptr, *tile_start = nullptr, *Sp = nullptr;
+    uint8_t *head = nullptr;
+    int *scalars = nullptr;            // [0] n_tiles, [1] ticket
+    unsigned long long *status = nullptr;
+    void *tmp = nullptr;
+    int32_t *Sj = nullptr; void *Sx = nullptr;
+    void release() {
+        dev_free(small); dev_free(big); dev_free(tile_start); dev_free(Sp); dev_free(head); dev_free(scalars); dev_free(status); dev_free(tmp);
+        ws_release(0, Sj); ws_release(1, Sx);
+        small = big = tile_start = Sp = nullptr; head = nullptr; scalars = nullptr; status = nullptr; tmp = nullptr; Sj = nullptr; Sx = nullptr;
+    }
+};
+
+// table / stage sizes from the shared-memory budget of `ctas` CTAs per SM; R = largest row bound hashed by the tile kernel,
+// W = flop window of a tile (a tile holds < W + R products, its slices <= tf8/8 (W + R) + 2 TILE_RMAX table entries)
+template <typename T> static TileCfg make_tile_cfg() {
+    TileCfg c;
+    const bool packed = Packed<T>::value && use_packed();
+    c.threads = (int)std::min<long>(512, std::max<long>(64, opt_get_int("spgemm_tile_threads", 256))) & ~31;
+    c.ctas = (int)std::min<long>(4, std::max<long>(1, opt_get_int("spgemm_tile_ctas", 2)));
+    c.scap = (int)std::max<long>(256, opt_get_int("spgemm_tile_scap", 1792)) & ~15;
+    c.tf8 = (int)std::max<long>(9, opt_get_int("spgemm_tile_tf8", 16));
+    const size_t budget = (size_t)(227 * 1024) / c.ctas - 1024 - 64;   // 1 KB per CTA is reserved by the driver
+    const size_t fixed = TileLayout<T>(0, c.scap, packed).total;
+    const size_t entry = packed ? 8 : 4 + sizeof(T);
+    if (budget < fixed + 4096 * entry) return c;   // not worth it
+    c.tcap = (int)((budget - fixed - 16) / entry) & ~63;
+    const long tc = opt_get_int("spgemm_tile_tcap", 0);
+    if (tc >= 1024 && tc < c.tcap) c.tcap = (int)tc & ~63;
+    // the largest row takes at most `spgemm_tile_rfrac8`/8 of the table; W = slot window of a tile, so that a tile's slices
+    // (rows starting inside one window) sum to < W + slice(R) <= tcap
+    const int64_t rslots = ((int64_t)c.tcap * std::min<long>(7, std::max<long>(1, opt_get_int("spgemm_tile_rfrac8", 5)))) / 8;
+    c.R = ((rslots - 34) * 8) / c.tf8;
+    const long ropt = opt_get_int("spgemm_tile_r", 0);
+    if (ropt > 0 && ropt < c.R) c.R = ropt;
+    if (c.R < 1) return c;
+    c.W = (int64_t)c.tcap - tile_slice_size(c.R, c.tf8);
+    if (c.W < 64) return c;
+    c.smem = TileLayout<T>(c.tcap, c.scap, packed).total;
+    c.on = true;
+    return c;
+}
+
+template <typename SR, typename T, bool PACK>
+static GrB_Info launch_tile_kernel(const SR &sr, const TileCfg &c, const TileArgs &ta, std::string *err) {
+    auto kern = spgemm_tile_kernel<SR, T, PACK>;
+    CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int per_sm = 0;
+    CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c.threads, c.smem));
+    if (per_sm < 1) return set_error(err, GrB_PANIC, "spgemm tile kernel does not fit an SM (%zu bytes of shared memory)", c.smem);
+    per_sm = std::min(per_sm, c.ctas);
+    LAUNCH_NOTE("spgemm_numeric_tile");
+    kern<<<(unsigned)(g_num_sms * per_sm), c.threads, c.smem, g_stream>>>(sr, ta);
+    CUDA_TRY(err, cudaGetLastError());
+    return GrB_SUCCESS;
+}
+
+template <typename T>
+static GrB_Info spgemm_tiled_typed(const GrB_Semiring op, const SpgemmPlan &p, const TileCfg &c, int64_t *flops, int64_t *row_nnz,
+                                   uint64_t total_flops, uint64_t big_flops, uint64_t n_big, TileScratch *x, Bins *bins, GrB_Matrix Tm,
+                                   int64_t *total_out, std::string *err) {
+    const int64_t m = p.m;
+    const size_t es = sizeof(T);
+    const unsigned blocks = (unsigned)std::min<int64_t>((m + 256) / 256, (int64_t)g_num_sms * 8);
+    // ---- 1. bounds of the rows the tile kernel hashes / of the hole rows, tile list in row order
+    x->small = dev_alloc_t<int64_t>((size_t)m + 1);
+    x->big = dev_alloc_t<int64_t>((size_t)m + 1);
+    x->head = dev_alloc_t<uint8_t>((size_t)m + 1);
+    x->tile_start = dev_alloc_t<int64_t>((size_t)m + 2);
+    x->scalars = dev_alloc_t<int>(4);
+    x->status = dev_alloc_t<unsigned long long>((size_t)m + 1);
+    if (!x->small || !x->big || !x->head || !x->tile_start || !x->scalars || !x->status) return set_error(err, GrB_OUT_OF_MEMORY, "spgemm tile arrays");
+    {
+        LAUNCH_NOTE("spgemm_tile_plan");
+        tile_small_flops_kernel<<<blocks, 256, 0, g_stream>>>(m, flops, c.R, c.tf8, x->small, x->big);
+    }
+    GRB_TRY(exclusive_scan_i64(x->small, m + 1, err));   // x->small is now the prefix Fs
+    {
+        LAUNCH_NOTE("spgemm_tile_plan");
+        tile_heads_kernel<<<blocks, 256, 0, g_stream>>>(m, x->small, c.W, x->head);
+        size_t tb = 0;
+        thrust::counting_iterator<int64_t> it(0);
+        CUDA_TRY(err, cub::DeviceSelect::Flagged(nullptr, tb, it, x->head, x->tile_start, x->scalars, (int)m, g_stream));
+        x->tmp = dev_alloc(tb);
+        if (!x->tmp) return set_error(err, GrB_OUT_OF_MEMORY, "spgemm tile scratch");
+        CUDA_TRY(err, cub::DeviceSelect::Flagged(x->tmp, tb, it, x->head, x->tile_start, x->scalars, (int)m, g_stream));
+        tile_sentinel_kernel<<<1, 1, 0, g_stream>>>(x->tile_start, x->scalars, m);
+        CUDA_TRY(err, cudaMemsetAsync(x->scalars + 1, 0, sizeof(int), g_stream));
+        CUDA_TRY(err, cudaMemsetAsync(x->status, 0, sizeof(unsigned long long) * ((size_t)m + 1), g_stream));
+    }
+    // ---- 2. hole rows: the binned kernels hash them into a staging area addressed by the prefix of their bounds
+    int64_t n_listed = 0;
+    if (n_big > 0) {
+        GRB_TRY(make_bins(bins, numeric_entry_bytes<T>(), m, x->big, err));
+        for (int b = 1; b < NBINS; b++) n_listed += (int64_t)bins->count[b];
+        x->Sp = dev_alloc_t<int64_t>((size_t)m + 1);
+        x->Sj = (int32_t *)ws_acquire(0, (size_t)big_flops * 4);
+        x->Sx = ws_acquire(1, (size_t)big_flops * es);
+        if (!x->Sp || !x->Sj || !x->Sx) return set_error(err, GrB_OUT_OF_MEMORY, "spgemm hole staging (%llu products)", (unsigned long long)big_flops);
+        note_launch("i64_copy");
+        i64_copy_kernel<<<blocks, 256, 0, g_stream>>>(x->Sp, x->big, m + 1);
+        GRB_TRY(exclusive_scan_i64(x->Sp, m + 1, err));
+        GRB_TRY(spgemm_numeric_typed<T>(op, p, *bins, x->big, row_nnz, x->Sp, x->Sj, x->Sx, MaskArgs{nullptr, nullptr, nullptr}, err));
+    }
+    // ---- 3. result arrays bounded by the flops; the tile kernel writes row pointers, columns and values in place
+    const size_t bound = (size_t)(total_flops > 0 ? total_flops : 1);
+    Tm->csr.idx = dev_alloc_t<int32_t>(bound);
+    Tm->csr.val = dev_alloc(bound * es);
+    if (!Tm->csr.idx || !Tm->csr.val) return set_error(err, GrB_OUT_OF_MEMORY, "mxm result bound needs %llu entries (%.1f GB)", (unsigned long long)bound, (double)bound * (4 + es) / 1e9);
+    GrB_Info info = GrB_SUCCESS;
+    const int T_code = type_code_of<T>();
+    GRB_DISPATCH_SEMIRING(op->add, op->mul, T, SRT, sr, {
+        const void *ax = nullptr, *bx = nullptr;
+        void *atmp = nullptr, *btmp = nullptr;
+        if (sr.reads_a()) info = cast_view(&ax, &atmp, p.A->val, p.a_type, T_code, p.annz, err);
+        if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
+        if (!info) {
+            TileArgs ta;
+            ta.Ap = p.A->ptr; ta.Aj = p.A->idx; ta.Ax = ax;
+            ta.Bp = p.B->ptr; ta.Bj = p.B->idx; ta.Bx = bx;
+            ta.flops = flops; ta.hole_nnz = row_nnz; ta.tile_start = x->tile_start; ta.n_tiles = x->scalars; ta.ticket = x->scalars + 1;
+            ta.status = x->status; ta.Cp = Tm->csr.ptr; ta.Cj = Tm->csr.idx; ta.Cx = Tm->csr.val; ta.nrows = m; ta.R = c.R;
+            ta.tcap = c.tcap; ta.scap = c.scap; ta.tf8 = c.tf8; ta.cas_first = opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0;
+            ta.poll = (int)opt_get_int("spgemm_tile_poll", 0);
+            ta.dbg = nullptr;
+            unsigned long long *dbg = nullptr;
+            if (opt_get_int("spgemm_tile_dbg", 0) != 0) {   // phase counters of the producer / first consumer warp, printed to stderr
+                dbg = dev_alloc_t<unsigned long long>(TD_N);
+                if (dbg) cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * TD_N, g_stream);
+                ta.dbg = dbg;
+            }
+            info = launch_tile_kernel<SRT, T, Packed<T>::value>(sr, c, ta, err);
+            if (dbg) {
+                unsigned long long h[TD_N];
+                cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, g_stream);
+                cudaStreamSynchronize(g_stream);
+                static const char *nm[TD_N] = {"c_wait_full", "c_insert", "c_scan", "c_lookback", "c_write", "c_bar", "p_wait_tile", "p_tile", "p_wait_empty", "p_load", "p_issue", "chunks", "tiles"};
+                fprintf(stderr, "[spgemm_tile] tcap %d scap %d R %lld W %lld threads %d ctas %d smem %zu |", c.tcap, c.scap, (long long)c.R, (long long)c.W, c.threads, c.ctas, c.smem);
+                for (int q = 0; q < TD_N; q++) fprintf(stderr, " %s=%.3g", nm[q], (double)h[q]);
+                fprintf(stderr, "\n");
+                dev_free(dbg);
+            }
+        }
+        dev_free(atmp);
+        dev_free(btmp);
+    });
+    GRB_TRY(info);
+    // ---- 4. hole rows into their place
+    if (n_listed > 0) {
+        LAUNCH_NOTE("spgemm_place_rows");
+        const unsigned pb = (unsigned)std::min<int64_t>((n_listed + 7) / 8, (int64_t)g_num_sms * 16);
+        place_rows_kernel<T><<<pb, 256, 0, g_stream>>>(bins->rows, n_listed, x->Sp, Tm->csr.ptr, row_nnz, x->Sj, (const T *)x->Sx, Tm->csr.idx, (T *)Tm->csr.val);
+        CUDA_TRY(err, cudaGetLastError());
+    }
+    const int64_t total = read_i64(Tm->csr.ptr + m);
+    Tm->nvals = total;
+    Tm->jumbled = true;
+    *total_out = total;
+    // ---- 5. a product that compresses well would keep most of the bound allocated for nothing: move it to exact arrays
+    if ((uint64_t)total + total_flops / 8 < total_flops && total_flops > ((uint64_t)1 << 18)) {
+        const size_t nv = (size_t)(total > 0 ? total : 1);
+        int32_t *nj = dev_alloc_t<int32_t>(nv);
+        void *nx = dev_alloc(nv * es);
+        if (nj && nx) {
+            CUDA_TRY(err, cudaMemcpyAsync(nj, Tm->csr.idx, (size_t)total * 4, cudaMemcpyDeviceToDevice, g_stream));
+            CUDA_TRY(err, cudaMemcpyAsync(nx, Tm->csr.val, (size_t)total * es, cudaMemcpyDeviceToDevice, g_stream));
+            dev_free(Tm->csr.idx); dev_free(Tm->csr.val);
+            Tm->csr.idx = nj; Tm->csr.val = nx;
+        } else {
+            dev_free(nj); dev_free(nx);   // keep the generous arrays
+        }
+    }
+    return GrB_SUCCESS;
 }
 
 GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, GrB_Matrix B, bool bt, const GrB_Matrix M,
@@ -1342,16 +994,19 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     int64_t *Sp = nullptr;
     int32_t *Sj = nullptr;
     void *Sx = nullptr;
-    int64_t *gsmall = nullptr, *gbig = nullptr, *ggroups = nullptr;   // grouped small rows (one-pass numeric)
-    int32_t *gsrows = nullptr;
-    unsigned long long *red = dev_alloc_t<unsigned long long>(2);
+    TileScratch tsx;   // tiled one-pass (spgemm_tile.cuh)
+    unsigned long long *red = dev_alloc_t<unsigned long long>(4);
     Bins fbins, nbins;
     GrB_Matrix Tm = nullptr;
     GrB_Info info = GrB_SUCCESS;
     if (!flops || !row_nnz || !red) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm row arrays");
-    unsigned long long hred[2] = {0, 0};
+    unsigned long long hred[4] = {0, 0, 0, 0};
+    // tiled one-pass (default for unmasked products of >= 4-byte domains): rows with a bound above tile.R are "holes"
+    TileCfg tile;
+    if (!symbolic_only && es >= 4 && opt_get_int("spgemm_tile", 1) != 0 && !(M && !mask_comp && opt_get_int("spgemm_mask", 1) != 0))
+        GRB_DISPATCH_TYPE(D, T, if constexpr (sizeof(T) >= 4) tile = make_tile_cfg<T>());
     if (!info) {
-        cudaMemsetAsync(red, 0, 16, g_stream);
+        cudaMemsetAsync(red, 0, 32, g_stream);
         cudaMemsetAsync(row_nnz, 0, sizeof(int64_t) * ((size_t)p.m + 1), g_stream);
         cudaMemsetAsync(flops, 0, sizeof(int64_t) * ((size_t)p.m + 1), g_stream);
     }
@@ -1363,9 +1018,9 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         }
         {
             LAUNCH_NOTE("reduce_sum_max");
-            reduce_sum_max_kernel<<<std::min(blocks, g_num_sms * 4), 256, 0, g_stream>>>(flops, p.m, red);
+            reduce_sum_max_kernel<<<std::min(blocks, g_num_sms * 4), 256, 0, g_stream>>>(flops, p.m, tile.on ? tile.R : INT64_MAX, red);
         }
-        cudaMemcpyAsync(hred, red, 16, cudaMemcpyDeviceToHost, g_stream);
+        cudaMemcpyAsync(hred, red, 32, cudaMemcpyDeviceToHost, g_stream);
         cudaStreamSynchronize(g_stream);
     }
     const uint64_t total_flops = hred[0];
@@ -1381,7 +1036,8 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             size_t free_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
         }
-        const double need = 2.0 * (double)total_flops * (double)(4 + es);
+        // staged one-pass: staging + result; tiled: flops-bounded result + staging of the hole rows only
+        const double need = tile.on ? ((double)total_flops + (double)hred[2]) * (double)(4 + es) : 2.0 * (double)total_flops * (double)(4 + es);
         const double avail = (double)total_b * 0.9 - (double)GrB_cuda_memory_in_use();
         onepass = !strcmp(mode, "onepass") || (!strcmp(mode, "auto") && need < 0.8 * avail);
         if (!strcmp(mode, "twopass")) onepass = false;
@@ -1456,70 +1112,17 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             if (e != cudaSuccess) info = cuda_fail(err, e, "masked spgemm compaction");
         }
         dev_free(mtmp); dev_free(mcnt); dev_free(Mj_stage); dev_free(Mx_stage);
+    } else if (!info && onepass && tile.on) {
+        // ---- tiled one-pass: rows hashed in row order, output written in place (spgemm_tile.cuh)
+        GrB_Info i3 = GrB_NOT_IMPLEMENTED;
+        GRB_DISPATCH_TYPE(D, T, if constexpr (sizeof(T) >= 4) i3 = spgemm_tiled_typed<T>(op, p, tile, flops, row_nnz, total_flops, hred[2], hred[3], &tsx, &fbins, Tm, &total, err));
+        info = i3;
     } else if (!info && onepass) {
         // ---- bins and tables from the flops bound; staging addressed by the flops prefix
         size_t entry = 12;
         GRB_DISPATCH_TYPE(D, T, entry = numeric_entry_bytes<T>());
         phase_mark("mxm_plan");
-        // rows with <= R products go to the grouped kernel (needs a >= 4-byte domain for its tables); the bins see the rest
-        GroupArgs ga;
         const int64_t *bin_cnt = flops;
-        if (es >= 4 && opt_get_int("spgemm_group", 0) != 0) {   // experimental, off by default: measured slower
-            const int64_t G = std::max<long>(512, opt_get_int("spgemm_group_g", 3072));
-            const int64_t R = std::min<int64_t>(G / 2, std::max<long>(1, opt_get_int("spgemm_group_r", 1024)));
-            ga.tf8 = (int)std::max<long>(9, opt_get_int("spgemm_group_tf8", 12));
-            ga.R = R;
-            ga.tslots = (int)((G * ga.tf8) >> 3) + 2 * GROUP_RMAX + 8;
-            ga.flops = flops;
-            gbig = dev_alloc_t<int64_t>((size_t)p.m + 1);
-            gsrows = dev_alloc_t<int32_t>((size_t)p.m + 1);
-            int *d_count = dev_alloc_t<int>(1);
-            void *tmp = nullptr;
-            if (!gbig || !gsrows || !d_count) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group arrays");
-            if (!info && group_smem_bytes(ga.tslots, es) > (size_t)226 * 1024) info = set_error(err, GrB_INVALID_VALUE, "spgemm_group_g too large for shared memory");
-            int n_small = 0;
-            if (!info) {
-                note_launch("split_flops");
-                split_flops_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, flops, R, gbig);
-                size_t tb = 0;
-                thrust::counting_iterator<int> it(0);
-                cub::DeviceSelect::If(nullptr, tb, it, gsrows, d_count, (int)p.m, SmallRowPred{flops, R}, g_stream);
-                tmp = dev_alloc(tb);
-                if (!tmp) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group scratch");
-                if (!info) {
-                    note_launch("small_rows");
-                    cudaError_t e = cub::DeviceSelect::If(tmp, tb, it, gsrows, d_count, (int)p.m, SmallRowPred{flops, R}, g_stream);
-                    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_small, d_count, sizeof(int), cudaMemcpyDeviceToHost, g_stream);
-                    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
-                    if (e != cudaSuccess) info = cuda_fail(err, e, "small-row list");
-                }
-            }
-            int64_t total_small = 0;
-            if (!info && n_small > 0) {
-                gsmall = dev_alloc_t<int64_t>((size_t)n_small + 1);
-                if (!gsmall) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group prefix");
-                if (!info) {
-                    note_launch("gather_small_flops");
-                    gather_small_flops_kernel<<<copy_blocks, 256, 0, g_stream>>>(n_small, gsrows, flops, gsmall);
-                    info = exclusive_scan_i64(gsmall, (int64_t)n_small + 1, err);
-                }
-                if (!info) total_small = read_i64(gsmall + n_small);
-            }
-            if (!info && total_small > 0) {
-                const int64_t window = G - R;
-                ga.n_groups = (total_small + window - 1) / window;
-                ggroups = dev_alloc_t<int64_t>((size_t)ga.n_groups + 1);
-                if (!ggroups) info = set_error(err, GrB_OUT_OF_MEMORY, "spgemm group starts");
-                if (!info) {
-                    note_launch("group_starts");
-                    group_starts_kernel<<<(unsigned)((ga.n_groups + 1 + 255) / 256), 256, 0, g_stream>>>(n_small, gsmall, window, ga.n_groups, ggroups);
-                    ga.g_start = ggroups;
-                    ga.small_rows = gsrows;
-                }
-            }
-            dev_free(d_count); dev_free(tmp);
-            bin_cnt = gbig;
-        }
         if (!info) info = make_bins(&fbins, entry, p.m, bin_cnt, err);
         phase_mark("mxm_bins");
         if (!info) {
@@ -1536,7 +1139,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         if (!info) {
             GrB_Info i3 = GrB_NOT_IMPLEMENTED;
             phase_mark("mxm_staging_alloc");
-            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, bin_cnt, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err, ga));
+            GRB_DISPATCH_TYPE(D, T, i3 = spgemm_numeric_typed<T>(op, p, fbins, bin_cnt, row_nnz, Sp, Sj, Sx, MaskArgs{nullptr, nullptr, nullptr}, err));
             info = i3;
             phase_mark("mxm_numeric_launch");
         }
@@ -1604,7 +1207,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     phase_mark("mxm_compact_launch");
     dev_free(flops); dev_free(row_nnz); dev_free(red); dev_free(fbins.rows); dev_free(nbins.rows);
     dev_free(Sp); ws_release(0, Sj); ws_release(1, Sx);
-    dev_free(gsmall); dev_free(gbig); dev_free(ggroups); dev_free(gsrows);
+    tsx.release();
     if (info || symbolic_only) {
         if (Tm) GrB_Matrix_free(&Tm);
         return info;

@@ -257,15 +257,20 @@ __global__ void reduce_partial_kernel(int64_t n, int op, const T *__restrict__ u
         } else {
             unsigned int b = 0; memcpy(&b, &acc, sizeof(T)); b = __shfl_down_sync(0xffffffffu, b, o); memcpy(&other, &b, sizeof(T));
         }
-        acc = binop<T>(op, acc, other);
-        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        // combine only sides that hold values: any(x, y) returns y, so an empty partner must not overwrite a real value
+        const unsigned long long ocnt = __shfl_down_sync(0xffffffffu, cnt, o);
+        if (ocnt) acc = cnt ? binop<T>(op, acc, other) : other;
+        cnt += ocnt;
     }
     if (lane == 0) { s_val[warp] = acc; s_cnt[warp] = cnt; }
     __syncthreads();
     if (threadIdx.x == 0) {
         T a = s_val[0];
         unsigned long long c = s_cnt[0];
-        for (int q = 1; q < (int)(blockDim.x >> 5); q++) { a = binop<T>(op, a, s_val[q]); c += s_cnt[q]; }
+        for (int q = 1; q < (int)(blockDim.x >> 5); q++) {
+            if (s_cnt[q]) a = c ? binop<T>(op, a, s_val[q]) : s_val[q];
+            c += s_cnt[q];
+        }
         partial[blockIdx.x] = a;
         pcount[blockIdx.x] = c;
     }
@@ -273,12 +278,15 @@ __global__ void reduce_partial_kernel(int64_t n, int op, const T *__restrict__ u
 
 // a scalar of any builtin type in its widest faithful representation
 struct WideScalar { double d; int64_t l; uint64_t ul; bool isf, isu; };
-template <typename T> static WideScalar fold_partials(const unsigned char *hp, int blocks, int opcode) {
+template <typename T> static WideScalar fold_partials(const unsigned char *hp, int blocks, int opcode, const unsigned long long *counts = nullptr) {
     T acc = monoid_identity<T>(opcode);
+    bool have = false;
     for (int b = 0; b < blocks; b++) {
+        if (counts && counts[b] == 0) continue;   // a block that saw no entry holds the identity, which is not neutral for ANY
         T x;
         memcpy(&x, hp + (size_t)b * sizeof(T), sizeof(T));
-        acc = binop<T>(opcode, acc, x);
+        acc = have ? binop<T>(opcode, acc, x) : x;
+        have = true;
     }
     WideScalar w;
     if constexpr (is_gbool<T>::value) { w.d = acc.v; w.l = acc.v; w.ul = acc.v; w.isf = false; w.isu = true; }
@@ -346,7 +354,7 @@ extern "C" GrB_Info GrB_cuda_Vector_reduce(void *val, GrB_Type val_type, const G
     u->nvals = (int64_t)total;
     // fold the per-block partials in block order on the host, then accum + cast into *val
     WideScalar ws;
-    GRB_DISPATCH_TYPE(mt, T, ws = fold_partials<T>(hp.data(), blocks, op->opcode));
+    GRB_DISPATCH_TYPE(mt, T, ws = fold_partials<T>(hp.data(), blocks, op->opcode, hc.data()));
     store_scalar(val, val_type->code, accum ? accum->opcode : OP_NONE, ws);
     return GrB_SUCCESS;
 }
@@ -438,18 +446,20 @@ extern "C" GrB_Info GrB_transpose(GrB_Matrix C, const GrB_Matrix Mask, const GrB
 
 static GrB_Info matrix_apply_common(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, int mode, int opcode, int optype,
                                     const void *scalar_host, int scalar_type, GrB_Matrix A, const GrB_Descriptor desc) {
+    // the matrix is the second input of a bind-1st apply (GrB_INP1 transposes it), the first input otherwise
+    const bool transposed = desc && (mode == 1 ? desc->t1 : desc->t0);
     CHECK_INIT();
     if (!valid(C)) return set_error(nullptr, GrB_UNINITIALIZED_OBJECT, "apply: output matrix is not initialised");
     if (!valid(A)) return set_error(&C->err, GrB_NULL_POINTER, "apply: null or uninitialised argument");
     if (Mask && !valid(Mask)) return set_error(&C->err, GrB_UNINITIALIZED_OBJECT, "apply: bad mask");
     OperandCsr src;
-    GRB_TRY(operand_csr(&src, A, desc && desc->t0, false));
+    GRB_TRY(operand_csr(&src, A, transposed, false));
     if (C->nrows != src.nrows || C->ncols != src.ncols || (Mask && (Mask->nrows != C->nrows || Mask->ncols != C->ncols)))
         return set_error(&C->err, GrB_DIMENSION_MISMATCH, "apply: C(%lldx%lld) vs A(%lldx%lld)", (long long)C->nrows, (long long)C->ncols,
                          (long long)src.nrows, (long long)src.ncols);
     const int64_t nv = A->nvals;
     GrB_Matrix T = nullptr;
-    GRB_TRY(matrix_with_pattern(&T, optype, src, nv, (desc && desc->t0) ? false : A->jumbled, &C->err));
+    GRB_TRY(matrix_with_pattern(&T, optype, src, nv, transposed ? false : A->jumbled, &C->err));
     const void *av = nullptr;
     void *atmp = nullptr;
     GrB_Info info = nv > 0 ? cast_view(&av, &atmp, src.c->val, A->type, optype, nv, &C->err) : GrB_SUCCESS;
@@ -634,11 +644,244 @@ extern "C" GrB_Info GrB_cuda_Matrix_reduce(void *val, GrB_Type val_type, const G
         GRB_DISPATCH_TYPE(mt, T, (reduce_partial_kernel<T><<<blocks, 256, 0, g_stream>>>(n, op->opcode, (const T *)av, nullptr, (T *)partial, pcount)));
     }
     std::vector<unsigned char> hp((size_t)blocks * 8);
+    std::vector<unsigned long long> hc((size_t)blocks);
     cudaMemcpyAsync(hp.data(), partial, (size_t)blocks * type_size(mt), cudaMemcpyDeviceToHost, g_stream);
+    cudaMemcpyAsync(hc.data(), pcount, (size_t)blocks * 8, cudaMemcpyDeviceToHost, g_stream);
     cudaError_t e = cudaStreamSynchronize(g_stream);
     dev_free(atmp); dev_free(partial); dev_free(pcount);
     CUDA_TRY(&A->err, e);
-    GRB_DISPATCH_TYPE(mt, T, ws = fold_partials<T>(hp.data(), blocks, op->opcode));
+    GRB_DISPATCH_TYPE(mt, T, ws = fold_partials<T>(hp.data(), blocks, op->opcode, hc.data()));
     store_scalar(val, val_type->code, accum ? accum->opcode : OP_NONE, ws);
     return GrB_SUCCESS;
+}
+
+// ================================================================== select with a builtin GrB_IndexUnaryOp, whole-object assign
+// select keeps the entries for which op(x, i, j, thunk) holds and leaves their values untouched
+// (reference core/vector.py:1560-1631, core/matrix.py:2560-2630; GraphBLAS C API 2.0 section 4.3.9).  For a vector j = 0.
+template <typename T>
+__device__ __forceinline__ bool index_op_keeps(int op, int64_t i, int64_t j, T x, T y, int64_t yi) {
+    switch (op) {
+        case IOP_TRIL: return j <= i + yi;
+        case IOP_TRIU: return j >= i + yi;
+        case IOP_DIAG: return j == i + yi;
+        case IOP_OFFDIAG: return j != i + yi;
+        case IOP_COLLE: return j <= yi;
+        case IOP_COLGT: return j > yi;
+        case IOP_ROWLE: return i <= yi;
+        case IOP_ROWGT: return i > yi;
+        case IOP_VALUEEQ: return cmpop<T>(OP_EQ, x, y);
+        case IOP_VALUENE: return cmpop<T>(OP_NE, x, y);
+        case IOP_VALUEGT: return cmpop<T>(OP_GT, x, y);
+        case IOP_VALUEGE: return cmpop<T>(OP_GE, x, y);
+        case IOP_VALUELT: return cmpop<T>(OP_LT, x, y);
+        case IOP_VALUELE: return cmpop<T>(OP_LE, x, y);
+        case IOP_ROWINDEX: return i + yi != 0;       // index-valued ops used as a predicate: result cast to bool
+        case IOP_COLINDEX: return j + yi != 0;
+        case IOP_DIAGINDEX: return j - i + yi != 0;
+    }
+    return false;
+}
+static inline bool index_op_positional(int op) { return op < IOP_VALUEEQ || op > IOP_VALUELE; }
+
+template <typename T>
+__global__ void vec_select_kernel(int64_t n, int op, T y, int64_t yi, const T *__restrict__ u, const uint8_t *__restrict__ up,
+                                  uint8_t *__restrict__ tp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) tp[i] = (up[i] && index_op_keeps<T>(op, i, 0, u ? u[i] : T(), y, yi)) ? 1 : 0;
+}
+
+extern "C" GrB_Info GrB_cuda_Vector_select(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                           const GrB_Vector u, const void *thunk, GrB_Type thunk_type, const GrB_Descriptor desc) {
+    CHECK_INIT();
+    if (!valid(w)) return set_error(nullptr, GrB_UNINITIALIZED_OBJECT, "select: output vector is not initialised");
+    if (!op || !valid(u) || !thunk || !thunk_type) return set_error(&w->err, GrB_NULL_POINTER, "select: null or uninitialised argument");
+    if (mask && !valid(mask)) return set_error(&w->err, GrB_UNINITIALIZED_OBJECT, "select: bad mask");
+    if (u->n != w->n || (mask && mask->n != w->n)) return set_error(&w->err, GrB_DIMENSION_MISMATCH, "select: sizes differ");
+    const int64_t n = w->n;
+    GRB_TRY(vector_ensure_arrays(u));
+    const bool positional = index_op_positional(op->opcode);
+    const int ct = positional ? u->type : op->type;   // the type the predicate compares in
+    const void *uv = u->vals;
+    void *utmp = nullptr;
+    if (!positional) GRB_TRY(cast_view(&uv, &utmp, u->vals, u->type, ct, n, &w->err));
+    int64_t yi = 0;
+    unsigned char ybuf[8] = {0};
+    host_cast(&yi, TC_INT64, thunk, thunk_type->code);
+    host_cast(ybuf, ct, thunk, thunk_type->code);
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    void *tv = dev_alloc(nn * type_size(u->type));
+    uint8_t *tp = (uint8_t *)dev_alloc(nn);
+    if (!tv || !tp) { dev_free(utmp); dev_free(tv); dev_free(tp); return set_error(&w->err, GrB_OUT_OF_MEMORY, "select result"); }
+    cudaError_t e = cudaSuccess;
+    if (n > 0) {
+        e = cudaMemcpyAsync(tv, u->vals, (size_t)n * type_size(u->type), cudaMemcpyDeviceToDevice, g_stream);
+        LAUNCH_NOTE("vec_select");
+        GRB_DISPATCH_TYPE(ct, T, {
+            T y;
+            memcpy(&y, ybuf, sizeof(T));
+            vec_select_kernel<T><<<grid_for(n), 256, 0, g_stream>>>(n, op->opcode, y, yi, positional ? nullptr : (const T *)uv, u->present, tp);
+        });
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    dev_free(utmp);
+    if (e != cudaSuccess) { dev_free(tv); dev_free(tp); return cuda_fail(&w->err, e, "select"); }
+    return vector_write_back(w, tv, tp, u->type, mask, accum, desc, true);
+}
+
+// matrix: a warp per row flags and counts the kept entries, a scan gives the row pointers, a second pass compacts
+// (order within a row is preserved, so a sorted operand gives a sorted result)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mat_select_flags_kernel(int64_t nrows, int op, T y, int64_t yi, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj,
+                        const T *__restrict__ Ax, uint8_t *__restrict__ keep, int64_t *__restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < nrows; w += nw) {
+        const int64_t b = Ap[w], e = Ap[w + 1];
+        int c = 0;
+        for (int64_t k0 = b; k0 < e; k0 += 32) {
+            const int64_t k = k0 + lane;
+            bool kp = false;
+            if (k < e) {
+                kp = index_op_keeps<T>(op, w, (int64_t)Aj[k], Ax ? Ax[k] : T(), y, yi);
+                keep[k] = kp ? 1 : 0;
+            }
+            c += __popc(__ballot_sync(0xffffffffu, kp));
+        }
+        if (lane == 0) cnt[w] = c;
+    }
+}
+template <typename U>
+__global__ void __launch_bounds__(256)
+mat_select_compact_kernel(int64_t nrows, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const U *__restrict__ Ax,
+                          const uint8_t *__restrict__ keep, const int64_t *__restrict__ Tp, int32_t *__restrict__ Tj, U *__restrict__ Tx) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < nrows; w += nw) {
+        const int64_t b = Ap[w], e = Ap[w + 1];
+        int64_t out = Tp[w];
+        for (int64_t k0 = b; k0 < e; k0 += 32) {
+            const int64_t k = k0 + lane;
+            const bool kp = k < e && keep[k];
+            const unsigned m = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const int64_t pos = out + __popc(m & ((1u << lane) - 1u));
+                Tj[pos] = Aj[k];
+                Tx[pos] = Ax[k];
+            }
+            out += __popc(m);
+        }
+    }
+}
+
+extern "C" GrB_Info GrB_cuda_Matrix_select(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_IndexUnaryOp op,
+                                           const GrB_Matrix A, const void *thunk, GrB_Type thunk_type, const GrB_Descriptor desc) {
+    CHECK_INIT();
+    if (!valid(C)) return set_error(nullptr, GrB_UNINITIALIZED_OBJECT, "select: output matrix is not initialised");
+    if (!op || !valid(A) || !thunk || !thunk_type) return set_error(&C->err, GrB_NULL_POINTER, "select: null or uninitialised argument");
+    if (Mask && !valid(Mask)) return set_error(&C->err, GrB_UNINITIALIZED_OBJECT, "select: bad mask");
+    OperandCsr src;
+    GRB_TRY(operand_csr(&src, A, desc && desc->t0, false));
+    if (C->nrows != src.nrows || C->ncols != src.ncols || (Mask && (Mask->nrows != C->nrows || Mask->ncols != C->ncols)))
+        return set_error(&C->err, GrB_DIMENSION_MISMATCH, "select: C(%lldx%lld) vs A(%lldx%lld)", (long long)C->nrows, (long long)C->ncols,
+                         (long long)src.nrows, (long long)src.ncols);
+    const int64_t m = src.nrows, nv = A->nvals;
+    const bool positional = index_op_positional(op->opcode);
+    const int ct = positional ? A->type : op->type;
+    int64_t yi = 0;
+    unsigned char ybuf[8] = {0};
+    host_cast(&yi, TC_INT64, thunk, thunk_type->code);
+    host_cast(ybuf, ct, thunk, thunk_type->code);
+    GrB_Matrix T = nullptr;
+    GRB_TRY(matrix_new_shell(&T, A->type, m, src.ncols));
+    T->csr.ptr = dev_alloc_t<int64_t>((size_t)m + 1);
+    uint8_t *keep = (uint8_t *)dev_alloc((size_t)(nv > 0 ? nv : 1));
+    const void *av = src.c->val;
+    void *atmp = nullptr;
+    GrB_Info info = (!T->csr.ptr || !keep) ? set_error(&C->err, GrB_OUT_OF_MEMORY, "select scratch") : GrB_SUCCESS;
+    if (!info && !positional && nv > 0) info = cast_view(&av, &atmp, src.c->val, A->type, ct, nv, &C->err);
+    const unsigned blocks = (unsigned)std::min<int64_t>((m + 7) / 8 + 1, (int64_t)g_num_sms * 16);
+    if (!info) {
+        cudaMemsetAsync(T->csr.ptr, 0, sizeof(int64_t) * ((size_t)m + 1), g_stream);
+        if (m > 0) {
+            LAUNCH_NOTE("mat_select_flags");
+            GRB_DISPATCH_TYPE(ct, T_, {
+                T_ y;
+                memcpy(&y, ybuf, sizeof(T_));
+                mat_select_flags_kernel<T_><<<blocks, 256, 0, g_stream>>>(m, op->opcode, y, yi, src.c->ptr, src.c->idx, positional ? nullptr : (const T_ *)av, keep, T->csr.ptr);
+            });
+        }
+        info = exclusive_scan_i64(T->csr.ptr, m + 1, &C->err);
+    }
+    int64_t total = 0;
+    if (!info) total = read_i64(T->csr.ptr + m);
+    if (!info) {
+        const size_t tn = (size_t)(total > 0 ? total : 1);
+        T->csr.idx = dev_alloc_t<int32_t>(tn);
+        T->csr.val = dev_alloc(tn * type_size(A->type));
+        T->nvals = total;
+        T->jumbled = (desc && desc->t0) ? false : A->jumbled;
+        if (!T->csr.idx || !T->csr.val) info = set_error(&C->err, GrB_OUT_OF_MEMORY, "select result");
+    }
+    if (!info && total > 0) {
+        LAUNCH_NOTE("mat_select_compact");
+        switch (type_size(A->type)) {
+            case 1: mat_select_compact_kernel<uint8_t><<<blocks, 256, 0, g_stream>>>(m, src.c->ptr, src.c->idx, (const uint8_t *)src.c->val, keep, T->csr.ptr, T->csr.idx, (uint8_t *)T->csr.val); break;
+            case 2: mat_select_compact_kernel<uint16_t><<<blocks, 256, 0, g_stream>>>(m, src.c->ptr, src.c->idx, (const uint16_t *)src.c->val, keep, T->csr.ptr, T->csr.idx, (uint16_t *)T->csr.val); break;
+            case 4: mat_select_compact_kernel<uint32_t><<<blocks, 256, 0, g_stream>>>(m, src.c->ptr, src.c->idx, (const uint32_t *)src.c->val, keep, T->csr.ptr, T->csr.idx, (uint32_t *)T->csr.val); break;
+            default: mat_select_compact_kernel<uint64_t><<<blocks, 256, 0, g_stream>>>(m, src.c->ptr, src.c->idx, (const uint64_t *)src.c->val, keep, T->csr.ptr, T->csr.idx, (uint64_t *)T->csr.val); break;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) info = cuda_fail(&C->err, e, "select");
+    }
+    dev_free(atmp);
+    dev_free(keep);
+    if (!info) info = matrix_write_back(C, T, Mask, accum, desc);
+    GrB_Matrix_free(&T);
+    return info;
+}
+
+// w<mask> accum= u / C<Mask> accum= A over GrB_ALL: the standard write-back with T = a copy of the operand
+extern "C" GrB_Info GrB_Vector_assign(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Vector u,
+                                      const GrB_Index *indices, GrB_Index, const GrB_Descriptor desc) {
+    CHECK_INIT();
+    if (!valid(w)) return set_error(nullptr, GrB_UNINITIALIZED_OBJECT, "assign: output vector is not initialised");
+    if (!valid(u)) return set_error(&w->err, GrB_NULL_POINTER, "assign: null or uninitialised argument");
+    if (mask && !valid(mask)) return set_error(&w->err, GrB_UNINITIALIZED_OBJECT, "assign: bad mask");
+    if (indices != nullptr && indices != GrB_ALL) return set_error(&w->err, GrB_NOT_IMPLEMENTED, "assign: only GrB_ALL is on this backend's path");
+    if (u->n != w->n || (mask && mask->n != w->n)) return set_error(&w->err, GrB_DIMENSION_MISMATCH, "assign: sizes differ");
+    GRB_TRY(vector_ensure_arrays(u));
+    const int64_t n = w->n;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    void *tv = dev_alloc(nn * type_size(u->type));
+    uint8_t *tp = (uint8_t *)dev_alloc(nn);
+    if (!tv || !tp) { dev_free(tv); dev_free(tp); return set_error(&w->err, GrB_OUT_OF_MEMORY, "assign"); }
+    if (n > 0) {
+        CUDA_TRY(&w->err, cudaMemcpyAsync(tv, u->vals, (size_t)n * type_size(u->type), cudaMemcpyDeviceToDevice, g_stream));
+        CUDA_TRY(&w->err, cudaMemcpyAsync(tp, u->present, (size_t)n, cudaMemcpyDeviceToDevice, g_stream));
+    }
+    return vector_write_back(w, tv, tp, u->type, mask, accum, desc, true);
+}
+extern "C" GrB_Info GrB_Matrix_assign(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Matrix A, const GrB_Index *rows,
+                                      GrB_Index, const GrB_Index *cols, GrB_Index, const GrB_Descriptor desc) {
+    CHECK_INIT();
+    if (!valid(C)) return set_error(nullptr, GrB_UNINITIALIZED_OBJECT, "assign: output matrix is not initialised");
+    if (!valid(A)) return set_error(&C->err, GrB_NULL_POINTER, "assign: null or uninitialised argument");
+    if ((rows != nullptr && rows != GrB_ALL) || (cols != nullptr && cols != GrB_ALL))
+        return set_error(&C->err, GrB_NOT_IMPLEMENTED, "assign: only GrB_ALL is on this backend's path");
+    OperandCsr src;
+    GRB_TRY(operand_csr(&src, A, desc && desc->t0, false));
+    if (C->nrows != src.nrows || C->ncols != src.ncols || (Mask && (Mask->nrows != C->nrows || Mask->ncols != C->ncols)))
+        return set_error(&C->err, GrB_DIMENSION_MISMATCH, "assign: C(%lldx%lld) vs A(%lldx%lld)", (long long)C->nrows, (long long)C->ncols,
+                         (long long)src.nrows, (long long)src.ncols);
+    GrB_Matrix T = nullptr;
+    GRB_TRY(matrix_with_pattern(&T, A->type, src, A->nvals, (desc && desc->t0) ? false : A->jumbled, &C->err));
+    if (A->nvals > 0)
+        CUDA_TRY(&C->err, cudaMemcpyAsync(T->csr.val, src.c->val, type_size(A->type) * (size_t)A->nvals, cudaMemcpyDeviceToDevice, g_stream));
+    GrB_Info info = matrix_write_back(C, T, Mask, accum, desc);
+    GrB_Matrix_free(&T);
+    return info;
 }

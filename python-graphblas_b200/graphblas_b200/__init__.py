@@ -43,8 +43,8 @@ def is_initialized():
 
 from . import operator as _operator  # noqa: E402
 
-unary, binary, monoid, semiring = _operator.unary, _operator.binary, _operator.monoid, _operator.semiring
-for _m in (unary, binary, monoid, semiring):
+unary, binary, monoid, semiring, select = _operator.unary, _operator.binary, _operator.monoid, _operator.semiring, _operator.select
+for _m in (unary, binary, monoid, semiring, select):
     _sys.modules[_m.__name__] = _m
 
 from .base import Recorder, replace  # noqa: E402
@@ -53,4 +53,4 @@ from .scalar import Scalar  # noqa: E402
 from .vector import Vector  # noqa: E402
 from . import cuda  # noqa: E402
 
-__all__ = ["Matrix", "Vector", "Scalar", "semiring", "binary", "monoid", "unary", "dtypes", "replace", "init", "cuda"]
+__all__ = ["Matrix", "Vector", "Scalar", "semiring", "binary", "monoid", "unary", "select", "dtypes", "replace", "init", "cuda"]

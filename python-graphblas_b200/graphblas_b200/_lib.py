@@ -85,7 +85,7 @@ class Lib:
         return val
 
     def __dir__(self):
-        return sorted(set(self._handles) | set(CONSTANTS))
+        return sorted(set(self._handles) | set(CONSTANTS) | {"GrB_ALL"})
 
 
 _lib = None

@@ -9,9 +9,10 @@ from . import operator
 from ._lib import GrB_Index, lib
 from .base import BaseExpression, BaseType, StructuralMask, ValueMask, call
 from .dtypes import BOOL, FP64, INT64, lookup_dtype, unify
-from .exceptions import NoValue
+from .exceptions import InvalidValue, NoValue
 from .scalar import Scalar, ScalarExpression
-from .vector import Vector, VectorExpression, _ptr, _Ref, ints_to_numpy_buffer, values_to_numpy_buffer
+from .vector import (Vector, VectorExpression, _CScalar, _monoid_identity, _ptr, _Ref, _scalar_dtype, ints_to_numpy_buffer,
+                     values_to_numpy_buffer)
 
 _name_counter = [0]
 _CSR, _CSC, _COO = 0, 1, 2
@@ -116,7 +117,12 @@ class Matrix(BaseType):
             dup_op = operator.get_typed_op(dup_op, self.dtype, kind="binary")
             if dup_op.opclass == "Monoid":
                 dup_op = dup_op.binaryop
-        call(f"GrB_Matrix_build_{self.dtype.name}", [self, _ptr(rows), _ptr(columns), _ptr(values), GrB_Index(n), dup_op])
+        try:
+            call(f"GrB_Matrix_build_{self.dtype.name}", [self, _ptr(rows), _ptr(columns), _ptr(values), GrB_Index(n), dup_op])
+        except InvalidValue:
+            if dup_op is None:   # reference core/matrix.py:680-681 raises ValueError here
+                raise ValueError("Duplicate indices found, must provide `dup_op` BinaryOp") from None
+            raise
 
     @classmethod
     def _from_csx(cls, fmt, indptr, indices, values, dtype, num, check_num, name):
@@ -278,22 +284,29 @@ class Matrix(BaseType):
         return _reduce_to_vector(self.T, op, "reduce_columnwise")
 
     def reduce_scalar(self, op=None, *, allow_empty=True):
-        """reference core/matrix.py:2703-2735"""
+        """reference core/matrix.py:2703-2760: GrB_Matrix_reduce_Monoid_Scalar into a GrB_Scalar, or (allow_empty=False)
+        GrB_Matrix_reduce_<T> into a C scalar"""
         op = operator.monoid.plus if op is None else op
         op = operator.get_typed_op(op, self.dtype, kind="monoid")
         if op.opclass != "Monoid":
             raise TypeError("reduce_scalar expects a Monoid")
         me = self
+        if allow_empty:
+            def run(out, accum):
+                call("GrB_Matrix_reduce_Monoid_Scalar", [out, accum, op, me, None])
+
+            return ScalarExpression(op.return_type, run=run)
 
         def thunk():
-            x = op.return_type.ctype()
-            nv = GrB_Index()
-            call("GrB_cuda_Matrix_reduce", [ctypes.byref(x), op.return_type, None, op, me, ctypes.byref(nv)])
-            if nv.value == 0 and allow_empty:
-                return None
+            x = op.return_type.ctype(op.return_type.np_type.type(_monoid_identity(op)).item())
+            call(f"GrB_Matrix_reduce_{op.return_type.name}", [ctypes.byref(x), None, op, me, None])
             return x.value
 
         return ScalarExpression(op.return_type, thunk)
+
+    def select(self, op, thunk=None):
+        """reference core/matrix.py:2560-2630"""
+        return _select(self, op, thunk)
 
     def mxv(self, other, op=None):
         """reference core/matrix.py:2233-2262"""
@@ -460,19 +473,43 @@ def _apply(self, op, right, left):
         return MatrixExpression("apply", "GrB_Matrix_apply", [self], op=op, nrows=self._nrows, ncols=self._ncols,
                                 at=self._is_transposed)
     scalar = right if right is not None else left
-    sdt = lookup_dtype(np.asarray(scalar).dtype) if not isinstance(scalar, (int, float, bool)) else \
-        (BOOL if isinstance(scalar, bool) else INT64 if isinstance(scalar, int) else FP64)
+    if isinstance(scalar, Scalar) and not scalar._is_cscalar:
+        sdt, carg, sfx = scalar.dtype, scalar, "Scalar"
+    else:
+        if isinstance(scalar, Scalar):
+            scalar = scalar.value
+        sdt = _scalar_dtype(scalar)
+        carg, sfx = _CScalar(scalar, sdt), sdt.name
     op = operator.get_typed_op(op, self.dtype, sdt, kind="binary")
     if op.opclass == "Monoid":
         op = op.binaryop
-    me = self
+    # reference core/matrix.py:2472 / 2518: f"GrB_Matrix_apply_BinaryOp1st_{T}" (C, Mask, accum, op, x, A, desc), 2nd: (..., A, y, desc)
+    base = self._matrix if self._is_transposed else self
+    # at = bt like the reference (core/matrix.py:2531-2532): the matrix is input 1 of bind-1st (GrB_INP1) and input 0 of bind-2nd
+    if left is not None:
+        return MatrixExpression("apply", f"GrB_Matrix_apply_BinaryOp1st_{sfx}", [carg, base], op=op, nrows=self._nrows,
+                                ncols=self._ncols, at=self._is_transposed, bt=self._is_transposed)
+    return MatrixExpression("apply", f"GrB_Matrix_apply_BinaryOp2nd_{sfx}", [base, carg], op=op, nrows=self._nrows, ncols=self._ncols,
+                            at=self._is_transposed, bt=self._is_transposed)
 
-    def run(out, mask, accum, desc):
-        x = sdt.ctype(scalar)
-        call("GrB_cuda_Matrix_apply_binop", [out, mask, accum, op, me, ctypes.byref(x), sdt, 1 if left is not None else 0, desc])
 
-    return MatrixExpression("apply", None, [], dtype=op.return_type, nrows=self._nrows, ncols=self._ncols, custom=run,
-                            at=self._is_transposed)
+def _select(self, op, thunk):
+    """reference core/matrix.py:2560-2630: GrB_Matrix_select_<T>(C, Mask, accum, op, A, thunk, desc)"""
+    if thunk is None:
+        thunk = 0
+    if isinstance(thunk, Scalar) and not thunk._is_cscalar:
+        tdt, carg, sfx = thunk.dtype, thunk, "Scalar"
+    else:
+        if isinstance(thunk, Scalar):
+            thunk = thunk.value
+        tdt = _scalar_dtype(thunk)
+        carg, sfx = _CScalar(thunk, tdt), tdt.name
+    op = operator.get_typed_op(op, self.dtype, tdt, kind="select")
+    if op.opclass != "SelectOp":
+        raise TypeError(f"select expects a SelectOp, got {op.opclass}")
+    base = self._matrix if self._is_transposed else self
+    return MatrixExpression("select", f"GrB_Matrix_select_{sfx}", [base, carg], op=op, dtype=self.dtype, nrows=self._nrows,
+                            ncols=self._ncols, at=self._is_transposed)
 
 
 def _mxv(self, other, op):

@@ -94,6 +94,18 @@ class Monoid(OpBase):
         return getattr(binary, self.name)
 
 
+class SelectOp(OpBase):
+    """IndexUnaryOps that return BOOL, usable in select (reference core/operator/select.py; builtin names regex-matched from
+    dir(lib) at select.py `_parse_config`).  Positional ones (tril, triu, diag, offdiag, colle, colgt, rowle, rowgt) ignore the
+    values and take an INT64 thunk; value comparisons (valueeq ... valuele) are typed like the entries."""
+    opclass = "SelectOp"
+    is_positional = False
+
+    def __call__(self, obj, thunk=None):
+        """select.tril(A, -1) == A.select(select.tril, -1) (reference core/operator/select.py:44-61)"""
+        return obj.select(self, thunk)
+
+
 class Semiring(OpBase):
     opclass = "Semiring"
 
@@ -118,6 +130,7 @@ unary = types.ModuleType("graphblas_b200.unary")
 binary = types.ModuleType("graphblas_b200.binary")
 monoid = types.ModuleType("graphblas_b200.monoid")
 semiring = types.ModuleType("graphblas_b200.semiring")
+select = types.ModuleType("graphblas_b200.select")
 
 _RENAME_BINARY = {"oneb": "pair", "div": "cdiv", "rdiv": "rcdiv"}
 _STRING_BINARY = {"+": "plus", "-": "minus", "*": "times", "/": "truediv", "&": "land", "|": "lor", "^": "lxor",
@@ -148,6 +161,8 @@ def initialize():
                         rf"ISEQ|ISNE|EQ|NE|GT|LT|GE|LE)_({_TYPES})$")
     re_bin_bool = re.compile(r"^GrB_(LOR|LAND|LXOR|LXNOR)$")
     re_un = re.compile(rf"^G[rx]B_(IDENTITY|AINV|MINV|ABS|ONE|LNOT|BNOT)_({_TYPES})$")
+    re_sel_pos = re.compile(r"^GrB_(TRIL|TRIU|DIAG|OFFDIAG|COLLE|COLGT|ROWLE|ROWGT)$")
+    re_sel_val = re.compile(rf"^GrB_(VALUEEQ|VALUENE|VALUEGT|VALUEGE|VALUELT|VALUELE)_({_TYPES})$")
     semiring_names = set()
     for n in names:
         m = re_sr_grb.match(n) or re_sr_gxb.match(n)
@@ -192,6 +207,20 @@ def initialize():
             op = _get(unary, UnaryOp, o.lower())
             dt = lookup_dtype(t)
             op._add(TypedOp(op, op.name, dt, dt, getattr(L, n), n, "UnaryOp"))
+            continue
+        m = re_sel_pos.match(n)
+        if m:   # one C object serves every entry type
+            op = _get(select, SelectOp, m.group(1).lower())
+            op.is_positional = True
+            for dt in dtypes._ALL:
+                op._add(TypedOp(op, op.name, dt, BOOL, getattr(L, n), n, "SelectOp"))
+            continue
+        m = re_sel_val.match(n)
+        if m:
+            o, t = m.groups()
+            op = _get(select, SelectOp, o.lower())
+            dt = lookup_dtype(t)
+            op._add(TypedOp(op, op.name, dt, BOOL, getattr(L, n), n, "SelectOp"))
     if hasattr(unary, "lnot") and BOOL not in unary.lnot._typed_ops:
         unary.lnot._add(TypedOp(unary.lnot, "lnot", BOOL, BOOL, L.GrB_LNOT, "GrB_LNOT", "UnaryOp"))
     # ---- coercions (reference operator/semiring.py:468-588, binary.py:387-388)
@@ -241,8 +270,13 @@ def initialize():
     _initialized = True
 
 
+# reference core/operator/select.py `_str_to_select`
+_STRING_SELECT = {"==": "valueeq", "!=": "valuene", ">": "valuegt", ">=": "valuege", "<": "valuelt", "<=": "valuele",
+                  "col<=": "colle", "col>": "colgt", "row<=": "rowle", "row>": "rowgt", "index<=": "rowle", "index>": "rowgt"}
+
+
 def from_string(string, kind):
-    ns = {"binary": binary, "monoid": monoid, "semiring": semiring, "unary": unary}[kind]
+    ns = {"binary": binary, "monoid": monoid, "semiring": semiring, "unary": unary, "select": select}[kind]
     s = string.strip()
     dtype = None
     m = re.match(r"^(.*)\[(\w+)\]$", s)
@@ -250,6 +284,8 @@ def from_string(string, kind):
         s, dtype = m.group(1).strip(), m.group(2)
     if kind in ("binary", "monoid"):
         s = _STRING_BINARY.get(s, s)
+    if kind == "select":
+        s = _STRING_SELECT.get(s.replace(" ", ""), s).lower()
     if kind == "semiring" and "." in s:
         a, b = s.split(".", 1)
         s = f"{_STRING_BINARY.get(a, a)}_{_STRING_BINARY.get(b, b)}"
@@ -273,7 +309,7 @@ def get_typed_op(op, dtype, dtype2=None, *, kind=None):
             return op
     if not isinstance(op, OpBase):
         raise TypeError(f"Unable to get typed operator from object with type {type(op)}")
-    if dtype2 is None:
+    if dtype2 is None or getattr(op, "is_positional", False):
         return op[dtype]
     if op._custom_dtype is not None:
         rv = op._custom_dtype(op, dtype, dtype2)

@@ -9,7 +9,7 @@ from . import operator
 from ._lib import GrB_Index, lib
 from .base import (BaseExpression, BaseType, ComplementedStructuralMask, StructuralMask, ValueMask, call)
 from .dtypes import BOOL, FP64, INT64, lookup_dtype, unify
-from .exceptions import DimensionMismatch, NoValue
+from .exceptions import DimensionMismatch, InvalidValue, NoValue
 from .scalar import Scalar, ScalarExpression
 
 _name_counter = [0]
@@ -125,7 +125,12 @@ class Vector(BaseType):
             dup_op = operator.get_typed_op(dup_op, self.dtype, kind="binary")
             if dup_op.opclass == "Monoid":
                 dup_op = dup_op.binaryop
-        call(f"GrB_Vector_build_{self.dtype.name}", [self, _ptr(indices), _ptr(values), GrB_Index(indices.shape[0]), dup_op])
+        try:
+            call(f"GrB_Vector_build_{self.dtype.name}", [self, _ptr(indices), _ptr(values), GrB_Index(indices.shape[0]), dup_op])
+        except InvalidValue:
+            if dup_op is None:   # reference core/vector.py build: same message as Matrix.build (core/matrix.py:680-681)
+                raise ValueError("Duplicate indices found, must provide `dup_op` BinaryOp") from None
+            raise
 
     def to_coo(self, dtype=None, *, indices=True, values=True, sort=True):
         n = self.nvals
@@ -198,16 +203,16 @@ class Vector(BaseType):
         return VectorExpression("apply", "GrB_Vector_apply", [self], op=operator.unary.identity[self.dtype], size=self._size)
 
     def _scalar_assign_expr(self, value):
+        """w(mask, accum)[:] = scalar -> GrB_Vector_assign_<T>(w, mask, accum, x, GrB_ALL, n, desc) (reference core/vector.py:2020-2035)"""
         if isinstance(value, Scalar):
+            if not value._is_cscalar:
+                return VectorExpression("assign", "GrB_Vector_assign_Scalar", [value, _All(), GrB_Index(self._size)],
+                                        dtype=value.dtype, size=self._size)
             value = value.value
         vt = INT64 if isinstance(value, (int, np.integer)) and not isinstance(value, (bool, np.bool_)) else \
             BOOL if isinstance(value, (bool, np.bool_)) else FP64
-
-        def run(out, mask, accum, desc):
-            x = vt.ctype(value)
-            call("GrB_cuda_Vector_assign_scalar", [out, mask, accum, ctypes.byref(x), vt, desc])
-
-        return VectorExpression("assign", None, [], dtype=vt, size=self._size, custom=run)
+        return VectorExpression("assign", f"GrB_Vector_assign_{vt.name}", [_CScalar(value, vt), _All(), GrB_Index(self._size)],
+                                dtype=vt, size=self._size)
 
     def vxm(self, other, op=None):
         """reference core/vector.py:1341-1378: w' = v' (+).(x) A ; `other` may be A.T (-> GrB_DESC_T1)."""
@@ -291,31 +296,55 @@ class Vector(BaseType):
             op = operator.get_typed_op(op, self.dtype, kind="unary")
             return VectorExpression("apply", "GrB_Vector_apply", [self], op=op, size=self._size)
         scalar = right if right is not None else left
-        sdt = lookup_dtype(np.asarray(scalar).dtype) if not isinstance(scalar, (int, float, bool)) else \
-            (BOOL if isinstance(scalar, bool) else INT64 if isinstance(scalar, int) else FP64)
+        if isinstance(scalar, Scalar) and not scalar._is_cscalar:   # a GrB_Scalar: ..._BinaryOp1st_Scalar / 2nd_Scalar
+            sdt, carg, sfx = scalar.dtype, scalar, "Scalar"
+        else:
+            if isinstance(scalar, Scalar):
+                scalar = scalar.value
+            sdt = _scalar_dtype(scalar)
+            carg, sfx = _CScalar(scalar, sdt), sdt.name
         op = operator.get_typed_op(op, self.dtype, sdt, kind="binary")
         if op.opclass == "Monoid":
             op = op.binaryop
-        me = self
+        # reference core/vector.py:1477 / 1523: f"GrB_Vector_apply_BinaryOp1st_{T}" (w, mask, accum, op, x, u, desc), 2nd: (..., u, y, desc)
+        if left is not None:
+            return VectorExpression("apply", f"GrB_Vector_apply_BinaryOp1st_{sfx}", [carg, self], op=op, size=self._size)
+        return VectorExpression("apply", f"GrB_Vector_apply_BinaryOp2nd_{sfx}", [self, carg], op=op, size=self._size)
 
-        def run(out, mask, accum, desc):
-            x = sdt.ctype(scalar)
-            call("GrB_cuda_Vector_apply_binop", [out, mask, accum, op, me, ctypes.byref(x), sdt, 1 if left is not None else 0, desc])
-
-        return VectorExpression("apply", None, [], dtype=op.return_type, size=self._size, custom=run)
+    def select(self, op, thunk=None):
+        """reference core/vector.py:1560-1631: keep the entries for which op(value, index, 0, thunk) holds.
+        One C call: GrB_Vector_select_<T>(w, mask, accum, op, u, thunk, desc)."""
+        if thunk is None:
+            thunk = 0
+        if isinstance(thunk, Scalar) and not thunk._is_cscalar:
+            tdt, carg, sfx = thunk.dtype, thunk, "Scalar"
+        else:
+            if isinstance(thunk, Scalar):
+                thunk = thunk.value
+            tdt = _scalar_dtype(thunk)
+            carg, sfx = _CScalar(thunk, tdt), tdt.name
+        op = operator.get_typed_op(op, self.dtype, tdt, kind="select")
+        if op.opclass != "SelectOp":
+            raise TypeError(f"select expects a SelectOp, got {op.opclass}")
+        return VectorExpression("select", f"GrB_Vector_select_{sfx}", [self, carg], op=op, dtype=self.dtype, size=self._size)
 
     def reduce(self, op=None, *, allow_empty=True):
+        """reference core/vector.py:1633-1690: GrB_Vector_reduce_Monoid_Scalar into a GrB_Scalar (an empty vector gives an empty
+        scalar); allow_empty=False reduces into a C scalar with GrB_Vector_reduce_<T> (an empty vector gives the identity)."""
         op = operator.monoid.plus if op is None else op
         op = operator.get_typed_op(op, self.dtype, kind="monoid")
         if op.opclass != "Monoid":
             raise TypeError("reduce expects a Monoid")
+        me = self
+        if allow_empty:
+            def run(out, accum):
+                call("GrB_Vector_reduce_Monoid_Scalar", [out, accum, op, me, None])
+
+            return ScalarExpression(op.return_type, run=run)
 
         def thunk():
-            x = op.return_type.ctype()
-            nv = GrB_Index()
-            call("GrB_cuda_Vector_reduce", [ctypes.byref(x), op.return_type, None, op, self, ctypes.byref(nv)])
-            if nv.value == 0 and allow_empty:
-                return None
+            x = op.return_type.ctype(op.return_type.np_type.type(_monoid_identity(op)).item())
+            call(f"GrB_Vector_reduce_{op.return_type.name}", [ctypes.byref(x), None, op, me, None])
             return x.value
 
         return ScalarExpression(op.return_type, thunk)
@@ -342,6 +371,52 @@ class Vector(BaseType):
         i1, v1 = self.to_coo()
         i2, v2 = other.to_coo()
         return bool(np.array_equal(i1, i2) and np.all(np.isclose(v1.astype(np.float64), v2.astype(np.float64), rtol=rel_tol, atol=abs_tol)))
+
+
+def _scalar_dtype(x):
+    if isinstance(x, (bool, np.bool_)):
+        return BOOL
+    if isinstance(x, (int, np.integer)) and not isinstance(x, np.generic):
+        return INT64
+    if isinstance(x, float):
+        return FP64
+    return lookup_dtype(np.asarray(x).dtype)
+
+
+def _monoid_identity(op):
+    """identity of a builtin monoid in its own type (what GrB_*_reduce_<T> leaves for an empty input)"""
+    name, t = op.parent.name, op.return_type.np_type
+    if name in ("plus", "lor", "lxor", "any"):
+        return 0
+    if name in ("times", "land", "lxnor", "eq"):
+        return 1
+    info = np.finfo(t) if t.kind == "f" else None
+    if name == "min":
+        return np.inf if info else (True if t.kind == "b" else np.iinfo(t).max)
+    if name == "max":
+        return -np.inf if info else (False if t.kind == "b" else np.iinfo(t).min)
+    return 0
+
+
+class _CScalar:
+    """a C scalar argument passed by value with its C type (the reference passes Scalar(is_cscalar=True)._carg)"""
+
+    def __init__(self, value, dtype):
+        self.value, self.dtype = value, dtype
+        self.name = repr(value)
+
+    @property
+    def _carg(self):
+        return self.dtype.ctype(self.dtype.np_type.type(self.value).item())
+
+
+class _All:
+    """GrB_ALL (reference core/utils.py: `_CArray`/lib.GrB_ALL for slice(None))"""
+    name = gb_name = "GrB_ALL"
+
+    @property
+    def _carg(self):
+        return lib().GrB_ALL
 
 
 class _Ref:

@@ -1,0 +1,236 @@
+"""GPU parity tests of the boundary rows added in round 2: select, GrB_Scalar results of
+reduce, the typed bind-1st / bind-2nd apply names, whole-object assign, Matrix_setElement.  Every call goes through the
+C-ABI under the name the reference formats; expected values come from the reference's own known answers
+(graphblas/tests/test_matrix.py:1238-1271) and from the oracle (oracle/semantics.py) on seeded random inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+import helpers as H
+from oracle import semantics as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import graphblas_b200 as gb
+
+    gb.init()
+    return gb
+
+
+def _fixture_A(gb):
+    d = G.load(G.A_M)
+    return gb.Matrix.from_coo(d["rows"], d["cols"], d["vals"], nrows=d["nrows"], ncols=d["ncols"]), d
+
+
+def _coo_equal(got, rows, cols, vals):
+    I, J, X = got.to_coo()
+    order = np.lexsort((cols, rows))
+    return (np.array_equal(I.astype(np.int64), np.asarray(rows)[order]) and np.array_equal(J.astype(np.int64), np.asarray(cols)[order])
+            and np.array_equal(X, np.asarray(vals)[order].astype(X.dtype)))
+
+
+def test_select_reference_known_answers(gb):
+    """reference graphblas/tests/test_matrix.py:1238-1271 (fixture A: :34-49)"""
+    A, _ = _fixture_A(gb)
+    for expr in (A.select(gb.select.valueeq, 3), A.select("==", 3), gb.select.valueeq(A, 3)):
+        assert _coo_equal(expr.new(), [0, 3, 3, 6], [3, 0, 2, 4], [3, 3, 3, 3])
+    for expr in (gb.select.colle(A, 2), A.select("col<=", 2)):
+        assert _coo_equal(expr.new(), [3, 0, 3, 5, 6], [0, 1, 2, 2, 2], [3, 2, 3, 1, 5])
+    assert _coo_equal(A.select("TRIU").new(), [0, 0, 1, 2, 4, 1], [1, 3, 4, 5, 5, 6], [2, 3, 8, 1, 7, 4])
+    for expr in (gb.select.rowle(A, 2), A.select("row<=", 2)):
+        assert _coo_equal(expr.new(), [0, 0, 1, 1, 2], [1, 3, 4, 6, 5], [2, 3, 8, 4, 1])
+    with pytest.raises(TypeError):
+        A.select(gb.binary.plus, 3)
+
+
+SELECT_CASES = [("tril", 0), ("tril", -2), ("triu", 1), ("diag", 0), ("diag", 3), ("offdiag", 0), ("colle", 7), ("colgt", 20),
+                ("rowle", 11), ("rowgt", 30), ("valueeq", 2), ("valuene", 0), ("valuegt", 1), ("valuege", -1), ("valuelt", 0.5),
+                ("valuele", 3)]
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64, np.int8, np.bool_])
+@pytest.mark.parametrize("op,thunk", SELECT_CASES)
+def test_matrix_select_vs_oracle(gb, op, thunk, dtype):
+    if dtype == np.bool_ and op.startswith("value") and not isinstance(thunk, int):
+        pytest.skip("fractional thunk for BOOL entries")
+    rng = np.random.default_rng(hash((op, str(dtype))) % 2**31)
+    m, n = 37, 45
+    r, c = H.random_coo(rng, m, n, 400)
+    v = H.random_values(rng, r.size, dtype)
+    A, Ao = gb.Matrix.from_coo(r, c, v, nrows=m, ncols=n), S.SpMat.from_coo(r, c, v, m, n)
+    mr, mc = H.random_coo(rng, m, n, 500)
+    mv = rng.integers(0, 2, mr.size).astype(bool)
+    M, Mo = gb.Matrix.from_coo(mr, mc, mv, nrows=m, ncols=n), S.SpMat.from_coo(mr, mc, mv, m, n)
+    cr, cc = H.random_coo(rng, m, n, 300)
+    cv = H.random_values(rng, cr.size, dtype)
+    sel = getattr(gb.select, op)
+    # plain
+    got = A.select(sel, thunk).new()
+    want = S.select(S.SpMat(m, n, np.dtype(dtype)), None, None, op, Ao, thunk)
+    assert _coo_equal(got, *want.to_coo()), (op, thunk)
+    # transposed input, value mask, accumulator, replace
+    At, Ato = gb.Matrix.from_coo(c, r, v, nrows=n, ncols=m), S.SpMat.from_coo(c, r, v, n, m)
+    C, Co = gb.Matrix.from_coo(cr, cc, cv, nrows=m, ncols=n), S.SpMat.from_coo(cr, cc, cv, m, n)
+    accum = "lor" if dtype == np.bool_ else "plus"
+    C(mask=~M.V, accum=getattr(gb.binary, accum), replace=True) << At.T.select(sel, thunk)
+    want = S.select(Co, Mo, accum, op, Ato, thunk, t0=True, complement=True, structure=False, replace=True)
+    assert _coo_equal(C, *want.to_coo()), (op, thunk, "masked")
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float32, np.uint8])
+@pytest.mark.parametrize("op,thunk", [("rowle", 40), ("rowgt", 10), ("valuegt", 0), ("valuene", 1), ("tril", -5), ("triu", 0)])
+def test_vector_select_vs_oracle(gb, op, thunk, dtype):
+    rng = np.random.default_rng(11)
+    n = 100
+    idx = np.unique(rng.integers(0, n, 60))
+    v = H.random_values(rng, idx.size, dtype)
+    u = gb.Vector.from_coo(idx, v, size=n)
+    uo = S.SpMat.from_coo(idx, np.zeros_like(idx), v, n, 1)
+    got = u.select(getattr(gb.select, op), thunk).new()
+    want = S.select(S.SpMat(n, 1, np.dtype(dtype)), None, None, op, uo, thunk)
+    wi, _, wx = want.to_coo()
+    gi, gx = got.to_coo()
+    assert np.array_equal(gi.astype(np.int64), wi) and np.array_equal(gx, wx.astype(gx.dtype)), (op, thunk)
+    # under a structural mask with an accumulator
+    w = gb.Vector.from_coo(idx[::2], v[::2], size=n)
+    m = gb.Vector.from_coo(idx[::3], np.ones(idx[::3].size, bool), size=n)
+    w(mask=m.S, accum=gb.binary.plus) << u.select(getattr(gb.select, op), thunk)
+    wo = S.SpMat.from_coo(idx[::2], np.zeros_like(idx[::2]), v[::2], n, 1)
+    mo = S.SpMat.from_coo(idx[::3], np.zeros_like(idx[::3]), np.ones(idx[::3].size, bool), n, 1)
+    want = S.select(wo, mo, "plus", op, uo, thunk, structure=True)
+    wi, _, wx = want.to_coo()
+    gi, gx = w.to_coo()
+    assert np.array_equal(gi.astype(np.int64), wi) and np.array_equal(gx, wx.astype(gx.dtype)), (op, thunk, "masked")
+
+
+@pytest.mark.parametrize("monoid,dtype", [("plus", np.int64), ("plus", np.float64), ("min", np.int32), ("max", np.float32), ("times", np.int64),
+                                          ("any", np.int64), ("any", np.float32), ("lor", np.bool_), ("land", np.bool_)])
+def test_reduce_into_grb_scalar(gb, monoid, dtype):
+    """GrB_{Vector,Matrix}_reduce_Monoid_Scalar (reference core/vector.py:1670, core/matrix.py:2750) incl. the ANY monoid on sparse
+    inputs (round-1 advisor finding: empty lanes must not overwrite a real value) and the empty case"""
+    rng = np.random.default_rng(3)
+    op = getattr(gb.monoid, monoid)
+    for n, k in ((10, 1), (1000, 7), (100000, 300)):
+        idx = np.unique(rng.integers(0, n, k))
+        v = H.random_values(rng, idx.size, dtype)
+        if monoid == "times":
+            v = np.where(v == 0, 1, v).astype(dtype) % 3 + 1
+        u = gb.Vector.from_coo(idx, v, size=n)
+        s = u.reduce(op).new()
+        assert s.is_grbscalar and not s.is_empty
+        if monoid == "any":
+            assert s.value in set(v.tolist()), (n, s.value)
+        else:
+            want = S.reduce_scalar(monoid, S.SpMat.from_coo(idx, np.zeros_like(idx), v, n, 1))
+            assert s.value == want.item(), (n, s.value, want)
+        A = gb.Matrix.from_coo(idx // 10, idx % 10, v, nrows=n // 10 + 1, ncols=10)
+        t = A.reduce_scalar(op).new()
+        if monoid == "any":
+            assert t.value in set(v.tolist())
+        else:
+            assert t.value == want.item()
+    empty = gb.Vector(dtype, 50)
+    assert empty.reduce(op).new().is_empty and empty.reduce(op).new().value is None
+    assert gb.Matrix(dtype, 5, 5).reduce_scalar(op).new().is_empty
+    if monoid == "plus":
+        assert empty.reduce(op, allow_empty=False).new().value == 0
+        s = gb.Scalar(dtype)
+        s << u.reduce(op)
+        first = s.value
+        s(gb.binary.plus) << u.reduce(op)          # accumulate into the GrB_Scalar
+        assert s.value == 2 * first
+        s(gb.binary.plus) << empty.reduce(op)      # empty result + accumulator: unchanged
+        assert s.value == 2 * first
+        s << empty.reduce(op)                      # empty result, no accumulator: cleared
+        assert s.is_empty
+    if monoid == "min":
+        assert empty.reduce(op, allow_empty=False).new().value == np.iinfo(np.int32).max
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float32])
+@pytest.mark.parametrize("opname", ["plus", "minus", "times", "min", "first", "second"])
+def test_apply_bind_typed_names_vs_oracle(gb, opname, dtype):
+    """GrB_{Vector,Matrix}_apply_BinaryOp1st/2nd_<T> and ..._Scalar (reference core/vector.py:1477-1525, core/matrix.py:2472-2520)"""
+    rng = np.random.default_rng(21)
+    m, n = 30, 26
+    r, c = H.random_coo(rng, m, n, 200)
+    v = H.random_values(rng, r.size, dtype)
+    A, Ao = gb.Matrix.from_coo(r, c, v, nrows=m, ncols=n), S.SpMat.from_coo(r, c, v, m, n)
+    op = getattr(gb.binary, opname)
+    sc = 3 if dtype == np.int64 else 2.5
+    with gb.Recorder() as rec:
+        left = A.apply(op, left=sc).new()
+        right = A.apply(op, right=sc).new()
+        tr = A.T.apply(op, left=sc).new()
+        grb = A.apply(op, right=gb.Scalar.from_value(sc)).new()
+    text = " ".join(rec.data)
+    tname = "INT64" if dtype == np.int64 else "FP64"
+    assert f"GrB_Matrix_apply_BinaryOp1st_{tname}(" in text and f"GrB_Matrix_apply_BinaryOp2nd_{tname}(" in text
+    assert "GrB_Matrix_apply_BinaryOp2nd_Scalar(" in text
+    D = np.result_type(dtype, np.int64 if dtype == np.int64 else np.float64)
+    for got, kw in ((left, dict(scalar_first=True)), (right, dict(scalar_first=False)), (grb, dict(scalar_first=False))):
+        want = S.apply(S.SpMat(m, n, D), None, None, opname, Ao, scalar=sc, **kw)
+        assert _coo_equal(got, *want.to_coo()), (opname, kw)
+    want = S.apply(S.SpMat(n, m, D), None, None, opname, Ao, scalar=sc, scalar_first=True, t0=True)
+    assert _coo_equal(tr, *want.to_coo()), (opname, "transposed bind-1st")
+    # vectors
+    idx = np.unique(rng.integers(0, 80, 40))
+    x = H.random_values(rng, idx.size, dtype)
+    u = gb.Vector.from_coo(idx, x, size=80)
+    uo = S.SpMat.from_coo(idx, np.zeros_like(idx), x, 80, 1)
+    with gb.Recorder() as rec:
+        l, r2 = u.apply(op, left=sc).new(), u.apply(op, right=sc).new()
+    assert f"GrB_Vector_apply_BinaryOp1st_{tname}(" in rec.data[0] and f"GrB_Vector_apply_BinaryOp2nd_{tname}(" in rec.data[1]
+    for got, first in ((l, True), (r2, False)):
+        want = S.apply(S.SpMat(80, 1, D), None, None, opname, uo, scalar=sc, scalar_first=first)
+        wi, _, wx = want.to_coo()
+        gi, gx = got.to_coo()
+        assert np.array_equal(gi.astype(np.int64), wi) and np.array_equal(gx, wx.astype(gx.dtype))
+
+
+def test_whole_object_assign_and_setelement(gb):
+    """GrB_Vector_assign / GrB_Matrix_assign with GrB_ALL (reference core/vector.py:1928, core/matrix.py:3300) and
+    GrB_Matrix_setElement_<T>"""
+    from graphblas_b200.base import call
+    from graphblas_b200._lib import GrB_Index, lib
+
+    rng = np.random.default_rng(8)
+    n = 64
+    ui, wi_, mi = (np.unique(rng.integers(0, n, k)) for k in (30, 25, 35))
+    uv, wv = rng.integers(1, 9, ui.size), rng.integers(1, 9, wi_.size)
+    u, w = gb.Vector.from_coo(ui, uv, size=n), gb.Vector.from_coo(wi_, wv, size=n)
+    m = gb.Vector.from_coo(mi, np.ones(mi.size, bool), size=n)
+    ALL = lib().GrB_ALL
+    # w<m.S> += u : inside the mask accumulate / insert, outside untouched
+    call("GrB_Vector_assign", [w, m, gb.binary.plus[gb.dtypes.INT64], u, ALL, GrB_Index(n), None])
+    uo = S.SpMat.from_coo(ui, np.zeros_like(ui), uv, n, 1)
+    wo = S.SpMat.from_coo(wi_, np.zeros_like(wi_), wv, n, 1)
+    mo = S.SpMat.from_coo(mi, np.zeros_like(mi), np.ones(mi.size, bool), n, 1)
+    want = S._write_back(wo, dict(uo.e), uo.dtype, mo, "plus", False, False, False)
+    oi, _, ox = want.to_coo()
+    gi, gx = w.to_coo()
+    assert np.array_equal(gi.astype(np.int64), oi) and np.array_equal(gx, ox)
+    # an empty GrB_Scalar assigned under a mask with replace deletes
+    e = gb.Scalar(gb.dtypes.INT64)
+    call("GrB_Vector_assign_Scalar", [w, m, None, e, ALL, GrB_Index(n), gb.base.descriptor_lookup(output_replace=True)])
+    assert w.nvals == 0
+    # matrix
+    r, c = H.random_coo(rng, 12, 9, 40)
+    A = gb.Matrix.from_coo(r, c, rng.integers(1, 9, r.size), nrows=12, ncols=9)
+    C = gb.Matrix(gb.dtypes.INT64, 9, 12)
+    call("GrB_Matrix_assign", [C, None, None, A, ALL, GrB_Index(9), ALL, GrB_Index(12), gb.base.descriptor_lookup(transpose_first=True)])
+    assert C.isequal(A.T.new())
+    # setElement: new entry, overwrite, bounds
+    k0 = C.nvals
+    free = [(i, j) for i in range(9) for j in range(12) if C[i, j].new().value is None][0]
+    call("GrB_Matrix_setElement_INT64", [C, ctypes.c_int64(77), GrB_Index(free[0]), GrB_Index(free[1])])
+    assert C.nvals == k0 + 1 and C[free].new() == 77
+    call("GrB_Matrix_setElement_FP64", [C, ctypes.c_double(5.9), GrB_Index(free[0]), GrB_Index(free[1])])
+    assert C.nvals == k0 + 1 and C[free].new() == 5
+    with pytest.raises(gb.exceptions.InvalidIndex):
+        call("GrB_Matrix_setElement_INT64", [C, ctypes.c_int64(1), GrB_Index(9), GrB_Index(0)])
