@@ -321,6 +321,24 @@ GrB_Info GrB_cuda_Matrix_build_transpose(GrB_Matrix A); /* prebuild + cache the 
 GrB_Info GrB_cuda_mxm_symbolic(GrB_Index *flops, GrB_Index *nvals_out, const GrB_Matrix A, const GrB_Matrix B,
                                const GrB_Descriptor desc);
 
+/* ------------------------------------------------------------------ fused multiply + exchange over peer memory
+ * (the per-iteration all-gather of the row-partitioned BFS / SSSP / PageRank, done by the SpMV
+ * epilogue itself with NVLink P2P stores instead of a separate NCCL collective).
+ * peer_alloc: cudaMalloc'd, zeroed, exportable with CUDA IPC; ipc_get / ipc_open move the mapping between the ranks of
+ * one node; Vector_wrap presents such a buffer (values + presence bytes) as a library vector;
+ * set_peer_targets(n, vals[], present[] (or NULL), offset, scale): from now on GrB_mxv / GrB_vxm also store every finished
+ * output position i at position offset + i of the n target vectors (values optionally multiplied by scale[i], a device
+ * array of the result type); n = 0 switches it off.  The targets must outlive the multiply; ordering between ranks
+ * (nobody reads a target before every writer's kernel has completed) is the caller's, e.g. the all-reduce of the
+ * convergence flag. */
+GrB_Info GrB_cuda_peer_alloc(void **ptr, size_t bytes);
+GrB_Info GrB_cuda_peer_free(void *ptr);
+GrB_Info GrB_cuda_ipc_get(void *ptr, unsigned char handle[64]);
+GrB_Info GrB_cuda_ipc_open(const unsigned char handle[64], void **ptr);
+GrB_Info GrB_cuda_ipc_close(void *ptr);
+GrB_Info GrB_cuda_Vector_wrap(GrB_Vector *v, GrB_Type type, GrB_Index n, void *vals, uint8_t *present);
+GrB_Info GrB_cuda_set_peer_targets(int n, void *const *vals, uint8_t *const *present, GrB_Index offset, const void *scale);
+
 /* streams / timing / options / introspection */
 GrB_Info GrB_cuda_set_stream(void *cuda_stream); /* NULL restores the library's own stream */
 void *GrB_cuda_get_stream(void);

@@ -30,10 +30,15 @@ static GrB_Info mat_vec_common(GrB_Vector w, const GrB_Vector mask, const GrB_Bi
         GRB_TRY(vector_ensure_arrays(mask));
         GRB_TRY(mask_effective_bytes(&mbytes, &mtmp, mask->present, mask->vals, mask->type, mask->n, structure, &w->err));
     }
-    const bool needs_epi = mask != nullptr || accum != nullptr || comp;
+    const PeerTargets *peer = g_peer.n > 0 ? &g_peer : nullptr;
+    const bool needs_epi = mask != nullptr || accum != nullptr || comp || peer;
     const bool can_fuse = needs_epi && w->type == op->type && (!accum || (accum->type == w->type && accum->ztype == accum->type)) &&
-                          opt_get_int("fuse_epilogue", 1) != 0;
-    VecEpiHost epi{w->vals, w->present, mbytes, mask != nullptr, comp, replace, accum ? accum->opcode : OP_NONE};
+                          (peer || opt_get_int("fuse_epilogue", 1) != 0);
+    if (peer && !can_fuse) {
+        dev_free(mtmp);
+        return set_error(&w->err, GrB_NOT_IMPLEMENTED, "fused multiply + peer exchange needs output, semiring and accumulator of one type");
+    }
+    VecEpiHost epi{w->vals, w->present, mbytes, mask != nullptr, comp, replace, accum ? accum->opcode : OP_NONE, peer};
     void *tv = nullptr;
     uint8_t *tp = nullptr;
     int64_t tl = 0;
@@ -41,6 +46,7 @@ static GrB_Info mat_vec_common(GrB_Vector w, const GrB_Vector mask, const GrB_Bi
     GrB_Info info = multiply_mat_vec_impl(&tv, &tp, &tl, op, A, use_transpose, u, flip, mbytes, comp, &w->err, can_fuse ? &epi : nullptr, &fused);
     dev_free(mtmp);
     GRB_TRY(info);
+    if (peer && !fused) { dev_free(tv); dev_free(tp); return set_error(&w->err, GrB_PANIC, "fused peer exchange did not run"); }
     if (fused) {
         vector_take_arrays(w, tv, tp, -1);
         return GrB_SUCCESS;
@@ -172,3 +178,14 @@ GRB_TYPED(UINT32, uint32_t, GrB_UINT32)
 GRB_TYPED(UINT64, uint64_t, GrB_UINT64)
 GRB_TYPED(FP32, float, GrB_FP32)
 GRB_TYPED(FP64, double, GrB_FP64)
+
+// ------------------------------------------------------------------ fused multiply + exchange over peer memory
+PeerTargets g_peer = {0, {nullptr}, {nullptr}, 0, nullptr};
+extern "C" GrB_Info GrB_cuda_set_peer_targets(int n, void *const *vals, uint8_t *const *present, GrB_Index offset, const void *scale) {
+    if (n < 0 || n > MAX_PEERS || (n > 0 && !vals)) return set_error(nullptr, GrB_INVALID_VALUE, "peer targets: 0..%d vectors", MAX_PEERS);
+    g_peer.n = n;
+    for (int k = 0; k < n; k++) { g_peer.vals[k] = vals[k]; g_peer.present[k] = present ? present[k] : nullptr; }
+    g_peer.offset = (int64_t)offset;
+    g_peer.scale = scale;
+    return GrB_SUCCESS;
+}

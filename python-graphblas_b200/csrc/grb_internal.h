@@ -90,6 +90,7 @@ struct GrB_Vector_opaque {
     void *vals;           // n * type_size   (nullptr until first data)
     uint8_t *present;     // n bytes, 1 = entry exists
     int64_t nvals;        // -1 = unknown (count lazily)
+    bool external = false;   // vals / present belong to the caller (GrB_cuda_Vector_wrap): never freed by the library
     std::string err;
 };
 
@@ -185,7 +186,14 @@ GrB_Info matrix_write_back(GrB_Matrix C, GrB_Matrix T, const GrB_Matrix M, const
 // mask_eff (nullable): byte per output position, rows/positions ruled out by the mask may be skipped.
 // epi (nullable): write-back parameters; when the traversal can finish each output position exactly once (pull
 // kernels) it is applied inside the kernel and *fused is set -- the returned arrays are then the FINAL output.
-struct VecEpiHost { const void *c_vals; const uint8_t *c_present; const uint8_t *mask; int has_mask, comp, replace, accum; };
+// Peer targets of a fused multiply + exchange (GrB_cuda_set_peer_targets): every finished output position `row` is also stored
+// at position offset + row of n remote (or local) vectors, straight from the kernel's epilogue -- the all-gather of the
+// row-partitioned iteration without a collective.  `scale` (optional, device array of the result type,
+// one value per local row) multiplies the value on its way out (PageRank exchanges damping * t / d, not t).
+constexpr int MAX_PEERS = 8;
+struct PeerTargets { int n; void *vals[MAX_PEERS]; uint8_t *present[MAX_PEERS]; int64_t offset; const void *scale; };
+extern PeerTargets g_peer;
+struct VecEpiHost { const void *c_vals; const uint8_t *c_present; const uint8_t *mask; int has_mask, comp, replace, accum; const PeerTargets *peer; };
 GrB_Info multiply_mat_vec_impl(void **t_vals, uint8_t **t_present, int64_t *t_len, const GrB_Semiring op, GrB_Matrix A,
                                bool use_transpose, GrB_Vector u, bool flip, const uint8_t *mask_eff, bool mask_comp,
                                std::string *err, const VecEpiHost *epi, bool *fused);

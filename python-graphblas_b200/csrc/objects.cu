@@ -237,8 +237,11 @@ GrB_Info vector_new_shell(GrB_Vector *v, int type, int64_t n) {
 }
 
 void vector_release(GrB_Vector v) {
-    dev_free(v->vals);
-    dev_free(v->present);
+    if (!v->external) {
+        dev_free(v->vals);
+        dev_free(v->present);
+    }
+    v->external = false;
     v->vals = nullptr;
     v->present = nullptr;
     v->nvals = 0;
@@ -263,8 +266,11 @@ GrB_Info vector_ensure_arrays(GrB_Vector v) {
 }
 
 void vector_take_arrays(GrB_Vector v, void *vals, uint8_t *present, int64_t nvals) {
-    if (v->vals != vals) dev_free(v->vals);
-    if (v->present != present) dev_free(v->present);
+    if (!v->external) {
+        if (v->vals != vals) dev_free(v->vals);
+        if (v->present != present) dev_free(v->present);
+    }
+    v->external = false;   // the new arrays are the library's
     v->vals = vals;
     v->present = present;
     v->nvals = nvals;
@@ -384,5 +390,22 @@ extern "C" GrB_Info GrB_cuda_Matrix_device_csr(const GrB_Matrix A, int64_t **Ap,
     if (Ap) *Ap = A->csr.ptr;
     if (Aj) *Aj = A->csr.idx;
     if (Ax) *Ax = A->csr.val;
+    return GrB_SUCCESS;
+}
+
+// A vector over caller-owned device arrays (values + presence bytes of n positions): the replicated input vector of the fused
+// multiply + exchange lives in an IPC-exportable cudaMalloc buffer the peers store into.  The library reads the arrays in
+// place and never frees them; nvals is recounted on demand (GrB_cuda_Vector_touch after remote writes).
+extern "C" GrB_Info GrB_cuda_Vector_wrap(GrB_Vector *v, GrB_Type type, GrB_Index n, void *vals, uint8_t *present) {
+    CHECK_INIT();
+    if (!v || !type || !vals || !present) return GrB_NULL_POINTER;
+    if (n > (GrB_Index)INT32_MAX) return GrB_NOT_IMPLEMENTED;
+    GrB_Vector w;
+    GRB_TRY(vector_new_shell(&w, type->code, (int64_t)n));
+    w->vals = vals;
+    w->present = present;
+    w->external = true;
+    w->nvals = -1;
+    *v = w;
     return GrB_SUCCESS;
 }

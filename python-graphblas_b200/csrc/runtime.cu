@@ -365,3 +365,38 @@ extern "C" GrB_Info GrB_cuda_timer_stop(float *ms) {
     if (ms) *ms = t;
     return GrB_SUCCESS;
 }
+
+// ------------------------------------------------------------------ peer-visible buffers (fused multiply + exchange)
+// cudaMallocAsync pool memory cannot be exported with CUDA IPC; buffers other ranks write into come from plain cudaMalloc.
+extern "C" GrB_Info GrB_cuda_peer_alloc(void **ptr, size_t bytes) {
+    CHECK_INIT();
+    if (!ptr) return GrB_NULL_POINTER;
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaMalloc of a peer buffer");
+    CUDA_TRY(nullptr, cudaMemsetAsync(*ptr, 0, bytes ? bytes : 16, g_stream));
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_peer_free(void *ptr) {
+    if (ptr) { cudaStreamSynchronize(g_stream); cudaFree(ptr); }
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_ipc_get(void *ptr, unsigned char handle[64]) {
+    if (!ptr || !handle) return GrB_NULL_POINTER;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(nullptr, cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_ipc_open(const unsigned char handle[64], void **ptr) {
+    CHECK_INIT();
+    if (!ptr || !handle) return GrB_NULL_POINTER;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(nullptr, cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_ipc_close(void *ptr) {
+    if (ptr) { cudaStreamSynchronize(g_stream); CUDA_TRY(nullptr, cudaIpcCloseMemHandle(ptr)); }
+    return GrB_SUCCESS;
+}

@@ -125,31 +125,52 @@ struct TileInfo { long long row0; long long a0; int nrows; int tile; int last; i
 
 // decoupled look-back (one full warp): publishes this tile's aggregate, returns the sum of all tiles before it and
 // publishes the inclusive prefix.  A status word carries flag and value together, so no fences are involved.
-__device__ __forceinline__ void tile_publish(unsigned long long *status, int tile, long long aggregate) {
-    volatile unsigned long long *st = status;
-    st[tile] = (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG) | (unsigned long long)aggregate;
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void tile_publish(unsigned long long *status, int tile, long long aggregate) {
+    lb_store(status + tile, (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG) | (unsigned long long)aggregate);
+}
+// One full warp.  The walk back is a chain of dependent L2 round trips, so every step looks at LB_WIN x 32 tiles at once.
+constexpr int LB_WIN = 4;
 __device__ __forceinline__ long long tile_lookback(unsigned long long *status, int tile, long long aggregate, int lane) {
-    volatile unsigned long long *st = status;
     if (tile == 0) return 0;
     long long excl = 0;
     int idx = tile - 1;
     while (true) {
-        const int my = idx - lane;
-        unsigned long long s;
+        unsigned long long s[LB_WIN];
+        bool pending;
         do {
-            s = my >= 0 ? st[my] : LB_FLAG_PREFIX;
-        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-        const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        const int first = pm ? __ffs(pm) - 1 : 31;
-        long long v = lane <= first ? (long long)(s & LB_MASK) : 0;
+            pending = false;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (pm) break;
-        idx -= 32;
+            for (int k = 0; k < LB_WIN; k++) {
+                const int my = idx - lane - 32 * k;
+                s[k] = my >= 0 ? lb_load(status + my) : LB_FLAG_PREFIX;
+            }
+#pragma unroll
+            for (int k = 0; k < LB_WIN; k++) pending |= (s[k] >> 62) == 0;
+        } while (__any_sync(0xffffffffu, pending));
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < LB_WIN; k++) {
+            if (done) break;
+            const unsigned pm = __ballot_sync(0xffffffffu, (s[k] >> 62) == 2);
+            const int first = pm ? __ffs(pm) - 1 : 31;
+            long long v = lane <= first ? (long long)(s[k] & LB_MASK) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            excl += v;
+            done = pm != 0;
+        }
+        if (done) break;
+        idx -= 32 * LB_WIN;
     }
-    if (lane == 0) st[tile] = LB_FLAG_PREFIX | (unsigned long long)(excl + aggregate);
+    if (lane == 0) lb_store(status + tile, LB_FLAG_PREFIX | (unsigned long long)(excl + aggregate));
     return excl;
 }
 

@@ -589,6 +589,7 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             long ratio = opt_get_int("push_ratio", 16);
             push = u->nvals * ratio <= A->nrows;
         }
+        if (a.epi && a.epi->peer) push = false;   // the fused exchange lives in the pull kernels' row emission
         if (!push) GRB_TRY(matrix_ensure_twin(A));
     }
     CsrArrays &M = (a.use_transpose && !push) ? A->twin : A->csr;
@@ -624,12 +625,19 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
                 // pull kernels finish every row exactly once: the write-back is applied there, in registers -- except for 8-byte
                 // values without a mask, where the segmented kernel (whose row emission would be uncoalesced with the write-back
                 // fused) plus the separate O(n) write-back pass beats the fused merge-path kernel (SSSP: 455 vs 580 us)
-                const bool unfuse = a.epi && !a.mask && !a.epi->has_mask && sizeof(T) >= 8 && !strcmp(opt_get("spmv", "auto"), "auto") &&
+                const bool unfuse = a.epi && !a.epi->peer && !a.mask && !a.epi->has_mask && sizeof(T) >= 8 && !strcmp(opt_get("spmv", "auto"), "auto") &&
                                     A->nvals >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_unfuse_wide", 1) != 0;
                 if (a.epi && !unfuse) {
                     epi.active = 1;
                     epi.c_vals = (const T *)a.epi->c_vals; epi.c_present = a.epi->c_present; epi.mask = a.epi->mask;
                     epi.has_mask = a.epi->has_mask; epi.comp = a.epi->comp; epi.replace = a.epi->replace; epi.accum = a.epi->accum;
+                    if (a.epi->peer) {
+                        const PeerTargets &pt = *a.epi->peer;
+                        epi.npeer = pt.n;
+                        epi.poff = pt.offset;
+                        epi.pscale = (const T *)pt.scale;
+                        for (int k = 0; k < pt.n; k++) { epi.pv[k] = (T *)pt.vals[k]; epi.pp[k] = pt.present[k]; }
+                    }
                     if (a.fused) *a.fused = true;
                 }
                 info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, u->n, up, kflip, a.mask,

@@ -56,6 +56,12 @@ template <typename T> __device__ __forceinline__ T shfl_any(T v, int src_lane) {
 template <typename T> struct VecEpi {
     const T *c_vals; const uint8_t *c_present; const uint8_t *mask;
     int active, has_mask, comp, replace, accum;
+    // fused exchange: the finished value also goes to position poff + row of npeer peer vectors (NVLink P2P stores)
+    int npeer;
+    long long poff;
+    const T *pscale;
+    T *pv[MAX_PEERS];
+    uint8_t *pp[MAX_PEERS];
 };
 template <typename T>
 __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, int tp, T *__restrict__ w_vals,
@@ -80,6 +86,14 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
     }
     w_vals[row] = zp ? z : T();
     w_present[row] = zp ? 1 : 0;
+    if (e.npeer) {
+        const T out = zp ? (e.pscale ? binop<T>(OP_TIMES, z, e.pscale[row]) : z) : T();
+#pragma unroll 1
+        for (int k = 0; k < e.npeer; k++) {
+            e.pv[k][e.poff + row] = out;
+            if (e.pp[k]) e.pp[k][e.poff + row] = zp ? 1 : 0;
+        }
+    }
 }
 
 

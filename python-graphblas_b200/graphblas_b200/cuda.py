@@ -244,3 +244,62 @@ def mxm_symbolic(A, B):
     f, n = GrB_Index(), GrB_Index()
     call("GrB_cuda_mxm_symbolic", [ctypes.byref(f), ctypes.byref(n), A, B, None])
     return f.value, n.value
+
+
+# ------------------------------------------------------------------ fused multiply + exchange over peer memory
+def peer_alloc(nbytes):
+    """zeroed cudaMalloc buffer that other ranks of the node can map with CUDA IPC; returns the device pointer (int)"""
+    p = ctypes.c_void_p()
+    call("GrB_cuda_peer_alloc", [ctypes.byref(p), ctypes.c_size_t(int(nbytes))])
+    return p.value
+
+
+def peer_free(ptr):
+    call("GrB_cuda_peer_free", [ctypes.c_void_p(ptr)])
+
+
+def ipc_handle(ptr):
+    h = (ctypes.c_ubyte * 64)()
+    call("GrB_cuda_ipc_get", [ctypes.c_void_p(ptr), h])
+    return bytes(h)
+
+
+def ipc_open(handle):
+    p = ctypes.c_void_p()
+    h = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    call("GrB_cuda_ipc_open", [h, ctypes.byref(p)])
+    return p.value
+
+
+def ipc_close(ptr):
+    call("GrB_cuda_ipc_close", [ctypes.c_void_p(ptr)])
+
+
+def vector_wrap(dtype, n, vals_ptr, present_ptr, *, name=None):
+    """a library Vector over caller-owned device arrays (never freed by the library)"""
+    from .vector import Vector
+
+    dtype = lookup_dtype(dtype)
+    h = ctypes.c_void_p()
+    out = Vector._from_handle(h, dtype, n, name)
+    call("GrB_cuda_Vector_wrap", [ctypes.byref(h), dtype, GrB_Index(n), ctypes.c_void_p(vals_ptr), ctypes.c_void_p(present_ptr)])
+    return out
+
+
+class peer_targets:
+    """with peer_targets(vals_ptrs, present_ptrs, offset, scale=None): w(accum) << A.mxv(x, semiring)
+    -- inside the block every finished output position i of a GrB_mxv / GrB_vxm is also stored at offset + i of the target
+    vectors (optionally multiplied by scale[i], a device pointer to values of the result type)."""
+
+    def __init__(self, vals_ptrs, present_ptrs, offset, scale=None):
+        n = len(vals_ptrs)
+        self._v = (ctypes.c_void_p * n)(*vals_ptrs)
+        self._p = (ctypes.c_void_p * n)(*present_ptrs) if present_ptrs is not None else None
+        self._n, self._off, self._scale = n, int(offset), scale
+
+    def __enter__(self):
+        call("GrB_cuda_set_peer_targets", [self._n, self._v, self._p, GrB_Index(self._off), ctypes.c_void_p(self._scale) if self._scale else None])
+        return self
+
+    def __exit__(self, *exc):
+        call("GrB_cuda_set_peer_targets", [0, None, None, GrB_Index(0), None])

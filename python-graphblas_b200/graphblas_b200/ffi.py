@@ -71,6 +71,8 @@ def _ctype_of(decl):
     decl = re.sub(r"\bconst\b", " ", decl).strip()
     if decl == "void":
         return None
+    if "[" in decl and "*" not in decl:   # array parameter: decays to a pointer
+        return ctypes.c_void_p
     if "*" in decl:
         base = decl.split("*")[0].strip()
         return ctypes.c_char_p if base == "char" and decl.count("*") == 1 else ctypes.c_void_p

@@ -408,6 +408,9 @@ class TransposedMatrix:
     def apply(self, op, right=None, *, left=None):
         return _apply(self, op, right, left)
 
+    def select(self, op, thunk=None):
+        return _select(self, op, thunk)
+
     def reduce_rowwise(self, op=None):
         return _reduce_to_vector(self, op, "reduce_rowwise")
 

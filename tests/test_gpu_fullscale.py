@@ -1,5 +1,6 @@
-"""Full-size (BASELINE.json scale-22) checks through size-independent properties -- the oracle cannot run these sizes
-in seconds, so the CUDA path is checked against identities that any correct implementation must satisfy:
+"""Full-size (BASELINE.json scale-22) checks.  (1) Entry-by-entry comparison with the ORACLE on a random row sample of the
+headline product (the bench's own fp32 inputs: pattern exact, values within the stated tolerance) and of the SSSP / PageRank
+multiplies; (2) size-independent identities that any correct implementation must satisfy on the whole result:
   * mxv with all-ones operands reproduces the degree vector exactly; merge-path and warp-per-row kernels agree bit-exactly;
   * mxm: nvals equals the symbolic count, flops equals sum_k deg_A_col(k)*deg_B_row(k), and the checksum of checksums
     C.1 == A.(A.1) holds exactly for small-integer values;
@@ -232,3 +233,112 @@ def test_lazy_sort_all_row_classes(gb, torch):
             want_c, order = torch.sort(cols[b:e].long())
             assert torch.equal(c2[b:e].long(), want_c), (dt, r)
             assert torch.equal(v2[b:e], vals[b:e][order]), (dt, r)
+
+
+# ------------------------------------------------------------------ oracle comparison on row samples of BASELINE's own configs
+def _host_csr(ip, c, v):
+    return ip.cpu().numpy(), c.cpu().numpy().astype(np.int64), v.cpu().numpy()
+
+
+def _sample_rows(hp, hc, hv, rows, ncols):
+    from oracle import bigref as R
+
+    rows = np.sort(rows)
+    lens = hp[rows + 1] - hp[rows]
+    ptr = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    idx = np.repeat(hp[rows] - ptr[:-1], lens) + np.arange(ptr[-1])
+    return rows, R.BigMat(ptr, hc[idx], hv[idx], rows.size, ncols)
+
+
+def test_mxm_headline_row_sample_vs_oracle(gb, torch):
+    """BASELINE configs[1] as bench.py runs it (R-MAT 2a, fp32 values U(0,1), plus_times): 50 000 random rows of C = A.A compared
+    with the oracle's sorted Gustavson product of those rows (oracle/grb_oracle.c, pinned to the reference's goldens).
+    Pattern: exact.  Values: |got - want| <= 1e-5 * sqrt(k) * sum|products| bound, stated as rtol = 1e-5 * sqrt(max row degree)
+    against the oracle's fp32 sum in ascending-k order (the hash accumulates in arbitrary order; the reference's own tolerance
+    for such comparisons is isclose's rel_tol 1e-7 on exactly representable sums, graphblas/core/matrix.py:417)."""
+    import bench
+    from oracle import bigref as R
+
+    ip, c, n = _rmat(torch, bench.RMAT_2A)
+    v = bench.values_torch(c.numel(), 43, torch.float32, device=c.device)
+    A = gb.cuda.matrix_from_device_csr(ip, c, v, n, n)
+    C = A.mxm(A, gb.semiring.plus_times).new()
+    gb.cuda.matrix_sort(C)
+    cp, cj, cx = gb.cuda.matrix_as_torch(C)
+    hp, hc, hv = _host_csr(ip, c, v)
+    rng = np.random.default_rng(3)
+    rows, As = _sample_rows(hp, hc, hv, rng.choice(n, size=50_000, replace=False), n)
+    want = R.mxm_T("plus_times", As, R.BigMat(hp, hc, hv, n, n))
+    rt = torch.as_tensor(rows, device=c.device)
+    starts, ends = cp[rt], cp[rt + 1]
+    lens = (ends - starts).cpu().numpy()
+    assert np.array_equal(lens, np.diff(want.indptr)), "row lengths differ from the oracle"
+    gather = torch.repeat_interleave(starts - torch.as_tensor(want.indptr[:-1], device=c.device), ends - starts) + torch.arange(int(want.indptr[-1]), device=c.device)
+    got_j = cj[gather].cpu().numpy().astype(np.int64)
+    got_x = cx[gather].cpu().numpy()
+    assert np.array_equal(got_j, want.indices), "column pattern differs from the oracle"
+    kmax = int((hp[1:] - hp[:-1]).max())
+    rtol = 1e-5 * np.sqrt(kmax)
+    err = np.abs(got_x.astype(np.float64) - want.values.astype(np.float64))
+    assert np.all(err <= rtol * np.abs(want.values.astype(np.float64))), float((err / np.abs(want.values)).max())
+    # the same rows through the opt-in tile kernel (spgemm_tile.cuh)
+    nvals_staged = C.nvals
+    del cp, cj, cx, C
+    gb.cuda.set_option("trim", "1")       # hand the library's cached 20 GB blocks back before the second product
+    gb.cuda.set_option("spgemm_tile", "1")
+    try:
+        C2 = A.mxm(A, gb.semiring.plus_times).new()
+        assert C2.nvals == nvals_staged
+        gb.cuda.matrix_sort(C2)
+        p2, j2, x2 = gb.cuda.matrix_as_torch(C2)
+        starts2, ends2 = p2[rt], p2[rt + 1]
+        assert np.array_equal((ends2 - starts2).cpu().numpy(), np.diff(want.indptr))
+        gather2 = torch.repeat_interleave(starts2 - torch.as_tensor(want.indptr[:-1], device=c.device), ends2 - starts2) + torch.arange(int(want.indptr[-1]), device=c.device)
+        assert np.array_equal(j2[gather2].cpu().numpy().astype(np.int64), want.indices)
+        err2 = np.abs(x2[gather2].cpu().numpy().astype(np.float64) - want.values.astype(np.float64))
+        assert np.all(err2 <= rtol * np.abs(want.values.astype(np.float64)))
+    finally:
+        gb.cuda.set_option("spgemm_tile", None)
+        gb.cuda.set_option("trim", "1")
+
+
+def test_sssp_and_pagerank_multiplies_row_sample_vs_oracle(gb, torch):
+    """configs 4 / 5 multiplies on the Graph500-skew matrix: int64 min_plus mxv (exact) and fp64 plus_second A'.mxv (rtol 1e-12:
+    fp64 sums of <= 1e5 positive terms) on 200 000 random output rows, against the oracle's row-dot mxv"""
+    import bench
+    from oracle import bigref as R
+
+    ip, c, n = _rmat(torch, bench.RMAT_2B)
+    g = torch.Generator(device=c.device); g.manual_seed(43)
+    w = torch.randint(1, 256, (c.numel(),), device=c.device, generator=g, dtype=torch.int64)
+    W = gb.cuda.matrix_from_device_csr(ip, c, w, n, n)
+    xi = torch.randint(0, 1000, (n,), device=c.device, generator=g, dtype=torch.int64)
+    pres = (torch.rand(n, device=c.device, generator=g) < 0.6).to(torch.uint8)
+    x = gb.cuda.vector_from_torch(xi, pres)
+    y = W.mxv(x, gb.semiring.min_plus).new()
+    yv, yp = _vec_to_torch(gb, torch, y)
+    hp, hc, hw = _host_csr(ip, c, w)
+    rng = np.random.default_rng(5)
+    rows, Ws = _sample_rows(hp, hc, hw, rng.choice(n, size=200_000, replace=False), n)
+    want = R.mxv_T("min_plus", Ws, R.BigVec(xi.cpu().numpy(), pres.cpu().numpy()))
+    rt = torch.as_tensor(rows, device=c.device)
+    assert np.array_equal(yp[rt].cpu().numpy(), want.present)
+    sel = want.present.astype(bool)
+    assert np.array_equal(yv[rt].cpu().numpy()[sel], want.vals[sel])
+    # PageRank multiply: r = A'.w with plus_second on fp64; columns of A = rows of the transposed CSR
+    ones = torch.ones(c.numel(), dtype=torch.float64, device=c.device)
+    Af = gb.cuda.matrix_from_device_csr(ip, c, ones, n, n)
+    wv = torch.rand(n, device=c.device, generator=g, dtype=torch.float64)
+    r = Af.T.mxv(gb.cuda.vector_from_torch(wv), gb.semiring.plus_second).new()
+    rv, rp = _vec_to_torch(gb, torch, r)
+    from graphblas_b200 import distributed as D
+
+    tp, tc, _ = D.transpose_csr_torch(ip, c, None, n)
+    htp, htc = tp.cpu().numpy(), tc.cpu().numpy().astype(np.int64)
+    rows, Ts = _sample_rows(htp, htc, np.ones(htc.size, dtype=np.float64), rng.choice(n, size=200_000, replace=False), n)
+    want = R.mxv_T("plus_second", Ts, R.BigVec(wv.cpu().numpy(), np.ones(n, np.uint8)))
+    rt = torch.as_tensor(rows, device=c.device)
+    assert np.array_equal(rp[rt].cpu().numpy(), want.present)
+    sel = want.present.astype(bool)
+    assert np.allclose(rv[rt].cpu().numpy()[sel], want.vals[sel], rtol=1e-12, atol=0)

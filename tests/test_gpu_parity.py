@@ -351,6 +351,87 @@ def test_mxm_all_bins(gb):
     assert ok, msg
 
 
+@pytest.mark.parametrize("opts", [{}, {"spgemm_tile_ctas": "1", "spgemm_tile_threads": "512"}, {"spgemm_tile_scap": "512", "spgemm_tile_tcap": "2048"}])
+@pytest.mark.parametrize("dtype,semiring", [(np.float32, "plus_times"), (np.int64, "min_plus"), (np.float64, "plus_second"), (np.int32, "any_pair")])
+def test_mxm_tiled_kernel_vs_oracle(gb, dtype, semiring, opts):
+    """The row-ordered TMA-staged tile kernel (option spgemm_tile=1, csrc/spgemm_tile.cuh): hole rows, tiles of many short rows,
+    rows spanning several ring stages, tables of two sizes -- pattern and values exact against the oracle"""
+    rng = np.random.default_rng(17)
+    n = 3000
+    deg = np.concatenate([np.zeros(300, int), rng.integers(1, 4, 1500), rng.integers(4, 60, 1000), rng.integers(60, 300, 190), np.full(10, 1200)])
+    rng.shuffle(deg)
+    rows = np.repeat(np.arange(n), deg)
+    cols = np.concatenate([rng.choice(n, size=d, replace=False) for d in deg if d])
+    v = rng.integers(1, 5, rows.size).astype(dtype)
+    A = gb.Matrix.from_coo(rows, cols, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(rows, cols, v, n, n)
+    want = R.mxm_T(semiring, Ab, Ab)
+    gb.cuda.set_option("spgemm_tile", "1")
+    for k, val in opts.items():
+        gb.cuda.set_option(k, val)
+    try:
+        C = A.mxm(A, getattr(gb.semiring, semiring)).new()
+        if semiring == "any_pair":
+            I, J, X = C.to_coo()
+            wi, wj, _ = want.to_coo()
+            assert np.array_equal(I.astype(np.int64), wi) and np.array_equal(J.astype(np.int64), wj) and np.all(X == 1)
+        else:
+            ok, msg = H.mat_equal(C, want)
+            assert ok, msg
+    finally:
+        gb.cuda.set_option("spgemm_tile", None)
+        for k in opts:
+            gb.cuda.set_option(k, None)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.float32, 2e-5), (np.float64, 1e-13)])
+@pytest.mark.parametrize("scale", [10, 13])
+@pytest.mark.parametrize("tile", ["0", "1"])
+def test_mxm_float_noninteger_values_tolerance(gb, scale, dtype, rtol, tile):
+    """The bench dtype with the bench's kind of values (U(0,1), not exactly summable): pattern exact, values within
+    rtol * sqrt(max row degree) of the oracle's ascending-k sum (the hash accumulates in arbitrary order).  The reference's
+    own tolerance for floating point comparisons is isclose's rel_tol (graphblas/core/matrix.py:417)."""
+    r, c, n = H.rmat_edges(scale, a=0.45, b=0.15, c=0.15, seed=7)
+    v = np.random.default_rng(2).random(r.size).astype(dtype)
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    want = R.mxm_T("plus_times", Ab, Ab)
+    gb.cuda.set_option("spgemm_tile", tile)
+    try:
+        C = A.mxm(A, gb.semiring.plus_times).new()
+    finally:
+        gb.cuda.set_option("spgemm_tile", None)
+    ok, msg = H.mat_equal(C, want, rtol=rtol * np.sqrt(np.diff(Ab.indptr).max()))
+    assert ok, msg
+
+
+@pytest.mark.parametrize("structure", [True, False])
+def test_mxm_complemented_mask_in_hash_rmat(gb, structure):
+    """C<!A.S> = A.A and C<!A.V> = A.A on R-MAT scale 14 (Graph500 skew: heavy rows reach the global-table bin): the mask rows are
+    loaded into the hash tables as forbidden columns, the unmasked product is never formed (csrc/spgemm.cu insert_comp);
+    exact against the oracle, and identical to the mask-after-multiply path (option spgemm_mask=0)."""
+    r, c, n = H.rmat_edges(14, seed=5)
+    rng = np.random.default_rng(4)
+    v = rng.integers(0, 3, r.size).astype(np.int64)      # zeros make the value mask differ from the structural one
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    want = R.mxm(R.BigMat.from_coo([], [], np.array([], dtype=np.int64), n, n), Ab, None, "plus_times", Ab, Ab, complement=True,
+                 structure=structure, replace=False)
+    mask = ~A.S if structure else ~A.V
+    C = A.mxm(A, gb.semiring.plus_times).new(mask=mask)
+    ok, msg = H.mat_equal(C, want)
+    assert ok, msg
+    gb.cuda.set_option("spgemm_mask", "0")
+    try:
+        C0 = A.mxm(A, gb.semiring.plus_times).new(mask=mask)
+    finally:
+        gb.cuda.set_option("spgemm_mask", None)
+    assert C0.isequal(C)
+    with gb.Recorder() as rec:
+        A.mxm(A, gb.semiring.plus_times).new(mask=mask)
+    assert "GrB_DESC_SC" in rec.data[-1] if structure else "GrB_DESC_C" in rec.data[-1]
+
+
 @pytest.mark.parametrize("scale", [10, 14])
 def test_rmat_parity(gb, scale):
     """R-MAT (Graph500 parameters): skewed degrees exercise merge-path carries across tiles and heavy SpGEMM rows."""

@@ -295,6 +295,17 @@ def test_bench_reference_arm_json_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "nnz-out/s" and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the arm must use every host core even when the launcher exports OMP_NUM_THREADS=1 (torch.distributed.run does)
+    import os
+
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--scale", "12", "--steps", "1", "--warmup", "1", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=str(root), env=env)
+    d2 = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d2["cpu_baseline"]["cores"] == d["cpu_baseline"]["cores"] and d2["config"] == d["config"]
+    import bench
+
+    assert d["config"]["workload"] == bench.WORKLOAD.format(scale=12)   # the same string the GPU arm prints: same_config
 
 
 def test_fast_cpu_baseline_matches_oracle():
