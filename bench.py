@@ -827,6 +827,39 @@ def run_scale25(gb, torch, dist, D, dev, rank, world, barrier, max_over_ranks, s
                   "row_blocks_per_rank": nblk, "note": "each block's result is counted and released before the next block is formed"}
     del blocks, B, indptr, cols, vals
     gb.cuda.set_option("trim", "1")
+    # (b) plus_times fp32 mxv on the Graph500-skew scale-25 matrix, rows by equal nnz, x all-gathered every iteration
+    ip2, c2, n2 = rmat_csr_torch(scale, RMAT_2B, 44, device=dev)
+    nb = D.row_blocks_by_nnz(ip2, world)
+    q0, q1 = nb[rank], nb[rank + 1]
+    p0, p1 = int(ip2[q0]), int(ip2[q1])
+    M = gb.cuda.matrix_from_device_csr((ip2[q0:q1 + 1] - p0).contiguous(), c2[p0:p1].contiguous(),
+                                       values_torch(p1 - p0, 45 + rank, torch.float32, device=dev), q1 - q0, n2)
+    nnz2 = c2.numel()
+    del ip2, c2
+    x = gb.cuda.vector_from_torch(values_torch(n2, 46, torch.float32, device=dev))
+    x_next = D.GatheredVector(gb, gb.dtypes.FP32, n2, nb, sparse=False) if world > 1 else None
+
+    def mxv_iter():
+        y = M.mxv(x, sr).new()
+        if world > 1:
+            x_next.gather(y)
+        return y
+
+    for _ in range(10):
+        mxv_iter()
+    barrier()
+    ev0.record()
+    for _ in range(20):
+        mxv_iter()
+    ev1.record()
+    barrier()
+    ms_mxv = max_over_ranks(ev0.elapsed_time(ev1)) / 20
+    bytes_local = (p1 - p0) * 8 + (q1 - q0 + 1) * 8 + n2 * 4 + (q1 - q0) * 5
+    out["mxv"] = {"workload": "R-MAT scale-25 (0.57,0.19,0.19,0.05) plus_times fp32 A.mxv(x), x dense, equal-nnz row blocks, x all-gathered per iteration",
+                  "nnz": nnz2, "ms_per_iter": ms_mxv, "nnz_per_s": nnz2 / (ms_mxv * 1e-3),
+                  "GB_per_s_all_ranks": sum_over_ranks(float(bytes_local)) / (ms_mxv * 1e-3) / 1e9}
+    del M, x, x_next
+    gb.cuda.set_option("trim", "1")
     w = run_workloads_partitioned(gb, torch, dist, dev, 25, rank, world, max_over_ranks, which=("pagerank",))
     out["pagerank"] = w.get("pagerank")
     out["pagerank_graph"] = {k: w[k] for k in ("graph", "n", "nnz", "partition", "exchange")}
