@@ -589,23 +589,36 @@ def run_ours(args):
         h2d = h_ptr.numel() * 8 + h_col.numel() * 4 + h_val.numel() * 4
         d2h = o_ptr.numel() * 8 + o_col.numel() * 4 + o_val.numel() * 4
 
-        def e2e_step():
+        def e2e_step(blocks):
             Ah = gb.cuda.matrix_from_host_csr32(h_ptr.numpy(), h_col.numpy(), h_val.numpy(), r1 - r0, n)
-            Ch = Ah.mxm(B if world > 1 else Ah, sr).new()
-            gb.cuda.matrix_export_host_csr32(Ch, o_ptr.numpy(), o_col.numpy(), o_val.numpy(), sort=False)
+            if blocks <= 1:   # one GrB_mxm, then one export
+                Ch = Ah.mxm(B if world > 1 else Ah, sr).new()
+                gb.cuda.matrix_export_host_csr32(Ch, o_ptr.numpy(), o_col.numpy(), o_val.numpy(), sort=False)
+            else:             # the product leaves the device in row blocks while later blocks are still being multiplied
+                gb.cuda.mxm_to_host_csr32(Ah, B if world > 1 else Ah, sr, o_ptr.numpy(), o_col.numpy(), o_val.numpy(), blocks=blocks)
 
-        e2e_step()
-        barrier()
-        t_e = time.perf_counter()
-        ev0.record()
-        for _ in range(reps):
-            e2e_step()
-        ev1.record()
-        barrier()
-        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+        def time_e2e(blocks):
+            e2e_step(blocks)
+            barrier()
+            t_e = time.perf_counter()
+            ev0.record()
+            for _ in range(reps):
+                e2e_step(blocks)
+            ev1.record()
+            barrier()
+            return max_over_ranks(ev0.elapsed_time(ev1)) / reps, (time.perf_counter() - t_e) * 1e3 / reps
+
+        ms_single, _ = time_e2e(1)
+        check = (int(o_ptr[-1]), float(o_val[: 1 << 20].double().sum()), int(o_col[: 1 << 20].long().sum()))
+        ms_e2e, wall_e2e = time_e2e(args.e2e_blocks)
+        check2 = (int(o_ptr[-1]), float(o_val[: 1 << 20].double().sum()), int(o_col[: 1 << 20].long().sum()))
         e2e = {"value": nnz_c / (ms_e2e * 1e-3), "unit": "nnz-out/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "wall_ms_per_step": (time.perf_counter() - t_e) * 1e3 / reps,
-               "api": "GrB_cuda_Matrix_import_csr32 / GrB_mxm / GrB_cuda_Matrix_export_csr32 (int32 column indices, pinned host buffers)"}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "wall_ms_per_step": wall_e2e,
+               "api": f"GrB_cuda_Matrix_import_csr32, then graphblas_b200.cuda.mxm_to_host_csr32: GrB_mxm on {args.e2e_blocks} row blocks, each exported "
+                      "with GrB_cuda_Matrix_export_csr32_async while the next is multiplied (int32 column indices, pinned host buffers)",
+               "single_call": {"ms_per_step": ms_single, "value": nnz_c / (ms_single * 1e-3),
+                               "api": "GrB_cuda_Matrix_import_csr32 / one GrB_mxm / GrB_cuda_Matrix_export_csr32"},
+               "same_result": check == check2 if world == 1 else None}
         del h_ptr, h_col, h_val, o_ptr, o_col, o_val
         # (2) what the reference's Matrix.from_csr / to_csr hand over (graphblas/core/matrix.py:992-1068, 1601-1645): uint64 index
         # arrays in pageable numpy memory through GrB_Matrix_import_FP32 / GrB_Matrix_export_FP32 -- the host mirror's from_csr / to_csr
@@ -880,6 +893,7 @@ def main():
     ap.add_argument("--no-workloads", action="store_true")
     ap.add_argument("--no-scale25", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--e2e-blocks", type=int, default=12)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -290,6 +290,10 @@ GrB_Info GrB_cuda_Matrix_import_csr32(GrB_Matrix *A, GrB_Type type, GrB_Index nr
                                       int on_device, int sorted);
 GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void *Ax, GrB_Index nvals_capacity,
                                       GrB_Matrix A, int sort);
+/* the same copies on a separate copy stream, ordered after the work enqueued so far: the D2H of one result overlaps the
+ * computation of the next.  Host arrays (pinned) and the matrix must stay alive until GrB_cuda_copy_sync() returns. */
+GrB_Info GrB_cuda_Matrix_export_csr32_async(int64_t *Ap, int32_t *Aj, void *Ax, GrB_Index nvals_capacity, GrB_Matrix A);
+GrB_Info GrB_cuda_copy_sync(void);
 /* raw device views (valid until the object is next modified) */
 GrB_Info GrB_cuda_Matrix_device_csr(const GrB_Matrix A, int64_t **Ap, int32_t **Aj, void **Ax);
 /* matrix element-wise operations, all on the device: the C-API-2.0 names the reference calls

@@ -193,10 +193,13 @@ GrB_Info matrix_write_back(GrB_Matrix C, GrB_Matrix T, const GrB_Matrix M, const
             GRB_TRY(mask_effective_bytes(&meff, &mtmp, nullptr, M->csr.val, M->type, M->nvals, false, &C->err));
     }
     const int64_t nrows = C->nrows;
-    GrB_Matrix R;
-    GRB_TRY(matrix_new_shell(&R, C->type, C->nrows, C->ncols));
+    GrB_Matrix R = nullptr;
+    {   // every exit below releases the mask bytes and the shell (round-1 advisor finding: early returns leaked them)
+        GrB_Info ri = matrix_new_shell(&R, C->type, C->nrows, C->ncols);
+        if (ri) { dev_free(mtmp); return ri; }
+    }
     int64_t *optr = dev_alloc_t<int64_t>((size_t)nrows + 1);
-    if (!optr) { dev_free(mtmp); delete R; return set_error(&C->err, GrB_OUT_OF_MEMORY, "write-back row pointers"); }
+    if (!optr) { dev_free(mtmp); GrB_Matrix_free(&R); return set_error(&C->err, GrB_OUT_OF_MEMORY, "write-back row pointers"); }
     GrB_Info info = GrB_SUCCESS;
     cudaMemsetAsync(optr + nrows, 0, sizeof(int64_t), g_stream);
     unsigned blocks = (unsigned)((nrows + 127) / 128);

@@ -61,15 +61,17 @@ struct CsrArrays {
     int pull_calls = 0;              // pull SpMV calls seen (the analysis is paid for on the second one)
     // auto mode of the pull SpMV (spmv.cu run_pull): timed trial of merge-path / segmented / segmented + hot-column cache on the
     // first multiplies with this CSR, per element-size class (<= 4 bytes, 8 bytes); the winner is kept
-    int pull_choice[2] = {0, 0};     // 0 undecided, 1 merge, 2 seg, 3 seg + hot columns
+    int pull_choice[2] = {0, 0};     // 0 undecided, 1 merge, 2 seg, 3 seg + hot columns, 4 column-banded
     int pull_stage[2] = {0, 0};      // next candidate to time
-    float pull_ms[2][3] = {{-1.f, -1.f, -1.f}, {-1.f, -1.f, -1.f}};
+    float pull_ms[2][4] = {{-1.f, -1.f, -1.f, -1.f}, {-1.f, -1.f, -1.f, -1.f}};
     // row-boundary metadata of the segmented pull SpMV (spmv_seg.cu), built on first use
     uint8_t *seg_flags = nullptr;    // bit (k & 7) of byte (k >> 3): entry k is the first of its row
     int32_t *seg_rows = nullptr;     // rows that have at least one entry, ascending
     int32_t *seg_tile_ord = nullptr; // per 128 entries: ordinal (in seg_rows) of the row in progress before the tile
     int64_t seg_nonempty = 0;
     int seg_state = 0;               // 0 not built, 1 built
+    // column-banded copy of this CSR for the banded pull SpMV (spmv_band.cu), per element-size class; built on first use
+    void *band_fmt[2] = {nullptr, nullptr};
 };
 
 struct GrB_Matrix_opaque {

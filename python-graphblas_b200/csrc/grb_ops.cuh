@@ -64,8 +64,12 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LAND: return (T)((x != 0) && (y != 0));
             case OP_LXOR: return (T)((x != 0) != (y != 0));
             case OP_LXNOR: return (T)((x != 0) == (y != 0));
-            case OP_ISEQ: return (T)(x == y);
-            case OP_ISNE: return (T)(x != y);
+            case OP_ISEQ: case OP_EQ: return (T)(x == y);   // comparison codes: 1 / 0 in T (callers that need BOOL use cmpop)
+            case OP_ISNE: case OP_NE: return (T)(x != y);
+            case OP_GT: return (T)(x > y);
+            case OP_LT: return (T)(x < y);
+            case OP_GE: return (T)(x >= y);
+            case OP_LE: return (T)(x <= y);
         }
         return x;
     } else {
@@ -92,8 +96,12 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LAND: return (T)((x != 0) && (y != 0));
             case OP_LXOR: return (T)((x != 0) != (y != 0));
             case OP_LXNOR: return (T)((x != 0) == (y != 0));
-            case OP_ISEQ: return (T)(x == y);
-            case OP_ISNE: return (T)(x != y);
+            case OP_ISEQ: case OP_EQ: return (T)(x == y);
+            case OP_ISNE: case OP_NE: return (T)(x != y);
+            case OP_GT: return (T)(x > y);
+            case OP_LT: return (T)(x < y);
+            case OP_GE: return (T)(x >= y);
+            case OP_LE: return (T)(x <= y);
         }
         return x;
     }

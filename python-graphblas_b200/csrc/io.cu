@@ -3,6 +3,7 @@
 // :1601-1645, :627-681, :525-594; core/vector.py:465-568).  On the device indices become
 // int32 columns / int64 row pointers; conversion happens once, here.
 #include <cub/cub.cuh>
+#include <thread>
 #include <vector>
 
 #include "grb_ops.cuh"
@@ -76,7 +77,8 @@ static GrB_Info import_csr_device(GrB_Matrix A, const uint64_t *dAp, const uint6
     if (nnz > 0) {
         note_launch("u64_to_i32");
         u64_to_i32_kernel<<<grid_for(nnz), 256, 0, g_stream>>>(A->csr.idx, dAi, nnz, (uint64_t)A->ncols, flag);
-        GRB_TRY(cast_array(A->csr.val, A->type, dAx, xtype, nnz, err));
+        GrB_Info ci = cast_array(A->csr.val, A->type, dAx, xtype, nnz, err);
+        if (ci) { dev_free(flag); return ci; }
     }
     int h = 0;
     cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, g_stream);
@@ -176,8 +178,77 @@ extern "C" GrB_Info GrB_Matrix_exportSize(GrB_Index *Ap_len, GrB_Index *Ai_len, 
     return GrB_SUCCESS;
 }
 
+// ---- large device -> pageable-host downloads (what the reference's to_csr hands us: plain numpy arrays).
+// A single cudaMemcpy into pageable memory runs at a few GB/s (the driver stages through one pinned buffer with one host thread)
+// and the uint64 widening of int32 indices would double the PCIe bytes.  Instead: the array crosses PCIe in its DEVICE width in
+// 128 MB chunks into two pinned buffers, and a handful of host threads widen / copy chunk k into the destination (taking its
+// page faults in parallel) while chunk k + 1 is in flight.
+static struct { void *buf[2]; size_t bytes; cudaEvent_t ev[2]; } g_pin = {{nullptr, nullptr}, 0, {nullptr, nullptr}};
+constexpr size_t PIN_CHUNK_BYTES = (size_t)128 << 20;
+static bool pinned_ready() {
+    if (g_pin.bytes) return true;
+    for (int q = 0; q < 2; q++) {
+        if (cudaHostAlloc(&g_pin.buf[q], PIN_CHUNK_BYTES, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_pin.ev[q], cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+    }
+    g_pin.bytes = PIN_CHUNK_BYTES;
+    return true;
+}
+// mode 0: plain copy of `es`-byte elements; 1: int32 -> uint64; 2: int64 -> uint64 (bit copy)
+static void host_chunk(void *dst, const void *src, int64_t n, size_t es, int mode) {
+    const int nt = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), (n + (1 << 20) - 1) >> 20);
+    auto work = [=](int t) {
+        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        if (mode == 1) {
+            const int32_t *s32 = (const int32_t *)src;
+            uint64_t *d = (uint64_t *)dst;
+            for (int64_t i = lo; i < hi; i++) d[i] = (uint64_t)(uint32_t)s32[i];
+        } else {
+            memcpy((char *)dst + (size_t)lo * es, (const char *)src + (size_t)lo * es, (size_t)(hi - lo) * es);
+        }
+    };
+    if (nt <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+}
+static GrB_Info download_pipelined(void *host, const void *dev, int64_t n, size_t dev_es, int mode, std::string *err) {
+    const size_t host_es = mode == 1 ? 8 : dev_es;
+    const int64_t per = (int64_t)(PIN_CHUNK_BYTES / dev_es);
+    const int64_t nchunks = (n + per - 1) / per;
+    std::thread worker[2];
+    cudaError_t e = cudaSuccess;
+    for (int64_t k = 0; k <= nchunks && e == cudaSuccess; k++) {
+        const int q = (int)(k & 1);
+        if (k < nchunks) {
+            if (worker[q].joinable()) worker[q].join();   // chunk k - 2 has left this pinned buffer
+            const int64_t off = k * per, cnt = std::min<int64_t>(per, n - off);
+            e = cudaMemcpyAsync(g_pin.buf[q], (const char *)dev + (size_t)off * dev_es, (size_t)cnt * dev_es, cudaMemcpyDeviceToHost, g_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(g_pin.ev[q], g_stream);
+        }
+        if (k >= 1 && e == cudaSuccess) {   // chunk k - 1 has landed: hand it to the host threads while chunk k is in flight
+            const int p = (int)((k - 1) & 1);
+            e = cudaEventSynchronize(g_pin.ev[p]);
+            const int64_t off = (k - 1) * per, cnt = std::min<int64_t>(per, n - off);
+            void *dst = (char *)host + (size_t)off * host_es;
+            const void *src = g_pin.buf[p];
+            if (e == cudaSuccess) worker[p] = std::thread([=]() { host_chunk(dst, src, cnt, dev_es, mode); });
+        }
+    }
+    for (int q = 0; q < 2; q++)
+        if (worker[q].joinable()) worker[q].join();
+    CUDA_TRY(err, e);
+    return GrB_SUCCESS;
+}
+
 static GrB_Info download_as_u64(GrB_Index *host, const void *dev, bool is32, int64_t n, std::string *err) {
     if (n <= 0) return GrB_SUCCESS;
+    if ((size_t)n * (is32 ? 4 : 8) >= PIN_CHUNK_BYTES / 2 && opt_get_int("export_pipelined", 1) != 0 && pinned_ready())
+        return download_pipelined(host, dev, n, is32 ? 4 : 8, is32 ? 1 : 2, err);
     uint64_t *tmp = dev_alloc_t<uint64_t>((size_t)n);
     if (!tmp) return set_error(err, GrB_OUT_OF_MEMORY, "export staging");
     note_launch("to_u64");
@@ -194,6 +265,12 @@ static GrB_Info download_vals(void *host, int host_type, const void *dev, int de
     const void *src;
     void *tmp;
     GRB_TRY(cast_view(&src, &tmp, dev, dev_type, host_type, n, err));
+    GrB_Info info = GrB_SUCCESS;
+    if ((size_t)n * type_size(host_type) >= PIN_CHUNK_BYTES / 2 && opt_get_int("export_pipelined", 1) != 0 && pinned_ready()) {
+        info = download_pipelined(host, src, n, type_size(host_type), 0, err);
+        dev_free(tmp);
+        return info;
+    }
     cudaError_t e = cudaMemcpyAsync(host, src, type_size(host_type) * (size_t)n, cudaMemcpyDeviceToHost, g_stream);
     dev_free(tmp);
     CUDA_TRY(err, e);
@@ -249,6 +326,34 @@ extern "C" GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void 
     if (Aj && A->nvals) CUDA_TRY(err, cudaMemcpyAsync(Aj, A->csr.idx, sizeof(int32_t) * (size_t)A->nvals, cudaMemcpyDeviceToHost, g_stream));
     if (Ax && A->nvals) CUDA_TRY(err, cudaMemcpyAsync(Ax, A->csr.val, type_size(A->type) * (size_t)A->nvals, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(err, cudaStreamSynchronize(g_stream));
+    return GrB_SUCCESS;
+}
+
+// ---- asynchronous export: the copies run on a separate copy stream, ordered after everything enqueued so far on the compute
+// stream, so the D2H of one result overlaps the computation of the next (a product formed in row blocks leaves the device at
+// PCIe speed while later blocks are still being multiplied).  The matrix and the (pinned) host arrays must stay alive until
+// GrB_cuda_copy_sync() returns.
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_copy_ev = nullptr;
+extern "C" GrB_Info GrB_cuda_Matrix_export_csr32_async(int64_t *Ap, int32_t *Aj, void *Ax, GrB_Index cap, GrB_Matrix A) {
+    CHECK_INIT();
+    if (!valid(A)) return GrB_UNINITIALIZED_OBJECT;
+    if ((GrB_Index)A->nvals > cap) return set_error(&A->err, GrB_INSUFFICIENT_SPACE, "export_csr32: capacity %llu < nvals %lld", (unsigned long long)cap, (long long)A->nvals);
+    GRB_TRY(matrix_materialize(A));
+    std::string *err = &A->err;
+    if (!g_copy_stream) {
+        CUDA_TRY(err, cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(err, cudaEventCreateWithFlags(&g_copy_ev, cudaEventDisableTiming));
+    }
+    CUDA_TRY(err, cudaEventRecord(g_copy_ev, g_stream));
+    CUDA_TRY(err, cudaStreamWaitEvent(g_copy_stream, g_copy_ev, 0));
+    if (Ap) CUDA_TRY(err, cudaMemcpyAsync(Ap, A->csr.ptr, sizeof(int64_t) * (size_t)(A->nrows + 1), cudaMemcpyDeviceToHost, g_copy_stream));
+    if (Aj && A->nvals) CUDA_TRY(err, cudaMemcpyAsync(Aj, A->csr.idx, sizeof(int32_t) * (size_t)A->nvals, cudaMemcpyDeviceToHost, g_copy_stream));
+    if (Ax && A->nvals) CUDA_TRY(err, cudaMemcpyAsync(Ax, A->csr.val, type_size(A->type) * (size_t)A->nvals, cudaMemcpyDeviceToHost, g_copy_stream));
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_copy_sync(void) {
+    if (g_copy_stream) CUDA_TRY(nullptr, cudaStreamSynchronize(g_copy_stream));
     return GrB_SUCCESS;
 }
 

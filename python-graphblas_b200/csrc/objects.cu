@@ -44,7 +44,7 @@ void csr_drop_hot(CsrArrays &c) {
     for (int q = 0; q < 2; q++) {
         c.pull_choice[q] = 0;
         c.pull_stage[q] = 0;
-        for (int k = 0; k < 3; k++) c.pull_ms[q][k] = -1.f;
+        for (int k = 0; k < 4; k++) c.pull_ms[q][k] = -1.f;
     }
 }
 
@@ -59,7 +59,9 @@ void csr_drop_seg(CsrArrays &c) {
     c.seg_state = 0;
 }
 
+void csr_drop_band(CsrArrays &c);   // spmv_band.cu
 void csr_free(CsrArrays &c) {
+    csr_drop_band(c);
     dev_free(c.ptr);
     dev_free(c.idx);
     dev_free(c.val);

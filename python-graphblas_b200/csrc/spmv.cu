@@ -427,7 +427,7 @@ static GrB_Info ensure_tiles(CsrArrays &c, int64_t nrows, int64_t nnz, int tile_
 template <typename SR, typename T>
 static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz, const T *avals, const T *x, int64_t x_len,
                          const uint8_t *xp, bool flip, const uint8_t *mask, bool mask_comp, T *t_vals,
-                         uint8_t *t_present, const VecEpi<T> &epi, std::string *err) {
+                         uint8_t *t_present, const VecEpi<T> &epi, std::string *err, int native_val_type = -1) {
     if (mrows == 0) return GrB_SUCCESS;
     const char *method = opt_get("spmv", "auto");
     bool use_rowwarp = !strcmp(method, "rowwarp") || (!strcmp(method, "auto") && mask != nullptr);
@@ -445,21 +445,34 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
     // merge-path / segmented / segmented + hot-column cache by a timed trial on the first multiplies with this CSR:
     // which one wins depends on the value width and on how the labels are laid out (natural R-MAT labels keep the hot
     // columns adjacent, so L1 already serves them; permuted labels make the shared-memory cache win by ~15 %).
-    int candidate = 1;   // 1 merge, 2 seg, 3 seg + hot columns
+    int candidate = 1;   // 1 merge, 2 seg, 3 seg + hot columns, 4 column-banded (spmv_band.cu)
     int trial_cls = -1;
     static cudaEvent_t trial_ev[2] = {nullptr, nullptr};
+    // the banded kernel reads the matrix values in place (no typecast copy) and produces plain T
+    const bool band_ok = native_val_type >= 0 && !epi.active && !flip && opt_get_int("spmv_band", 1) != 0;
+    const int n_cand = band_ok && nnz >= opt_get_int("spmv_band_min_nnz", 1 << 22) ? 4 : 3;
     if (!strcmp(method, "seg")) candidate = 2;
+    else if (!strcmp(method, "band")) candidate = band_ok ? 4 : 1;
     else if (!strcmp(method, "auto") && !epi.active) {
         const int cls = sizeof(T) >= 8 ? 1 : 0;
         candidate = cls ? 2 : 1;
         const char *hot_opt = opt_get("spmv_hot", "auto");
         if (!strcmp(hot_opt, "1")) candidate = 2;   // forced cache: segmented kernel, spmv_seg_run honours the option
         else if (SR::kStatic && nnz >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_trial", 1) != 0) {
-            if (M.pull_choice[cls]) candidate = M.pull_choice[cls];
+            if (M.pull_choice[cls] && (M.pull_choice[cls] != 4 || band_ok)) candidate = M.pull_choice[cls];
+            else if (M.pull_choice[cls]) candidate = cls ? 2 : 1;   // the banded winner does not apply to this call
             else {
                 candidate = 1 + M.pull_stage[cls] / 2;   // every candidate runs twice: once to set up its cached metadata, once timed
-                if (candidate == 3 && !strcmp(hot_opt, "0")) {   // cache switched off: decide between the first two now
-                    M.pull_choice[cls] = M.pull_ms[cls][1] < M.pull_ms[cls][0] ? 2 : 1;
+                if (candidate == 3 && !strcmp(hot_opt, "0")) {   // cache switched off: skip its two stages
+                    M.pull_ms[cls][2] = 1e30f;
+                    M.pull_stage[cls] = 6;
+                    candidate = 4;
+                }
+                if (candidate > n_cand) {   // nothing left to try: settle
+                    int best = 0;
+                    for (int k = 1; k < 4; k++)
+                        if (M.pull_ms[cls][k] >= 0.f && (M.pull_ms[cls][best] < 0.f || M.pull_ms[cls][k] < M.pull_ms[cls][best])) best = k;
+                    M.pull_choice[cls] = best + 1;
                     candidate = M.pull_choice[cls];
                 } else {
                     trial_cls = cls;
@@ -485,14 +498,23 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
             return;
         }
         const int stage = M.pull_stage[trial_cls] / 2;
-        M.pull_ms[trial_cls][stage] = (stage == 2 && ran != 3) ? 1e30f : ms;   // cache not viable: candidate 3 cannot win
-        if (++M.pull_stage[trial_cls] == 6) {
+        M.pull_ms[trial_cls][stage] = (stage + 1 != ran) ? 1e30f : ms;   // the candidate did not apply and another kernel ran: it cannot win
+        if (++M.pull_stage[trial_cls] >= 2 * n_cand) {
             int best = 0;
-            for (int k = 1; k < 3; k++)
+            for (int k = 1; k < n_cand; k++)
                 if (M.pull_ms[trial_cls][k] < M.pull_ms[trial_cls][best]) best = k;
             M.pull_choice[trial_cls] = best + 1;
         }
     };
+    if (candidate == 4) {
+        bool handled = false;
+        GRB_TRY(spmv_band_run(type_code_of<T>(), sr.add_op(), sr.mul_op(), M, mrows, x_len, nnz, native_val_type, x, xp, t_vals, t_present,
+                              err, &handled));
+        if (handled) {
+            finish_trial(4);
+            return GrB_SUCCESS;
+        }
+    }
     if (candidate >= 2) {
         bool handled = false, used_hot = false;
         const int hot_mode = !strcmp(method, "seg") || !strcmp(opt_get("spmv_hot", "auto"), "1") ? -1 : (candidate == 3 ? 1 : 0);
@@ -625,8 +647,13 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
                 // pull kernels finish every row exactly once: the write-back is applied there, in registers -- except for 8-byte
                 // values without a mask, where the segmented kernel (whose row emission would be uncoalesced with the write-back
                 // fused) plus the separate O(n) write-back pass beats the fused merge-path kernel (SSSP: 455 vs 580 us)
-                const bool unfuse = a.epi && !a.epi->peer && !a.mask && !a.epi->has_mask && sizeof(T) >= 8 && !strcmp(opt_get("spmv", "auto"), "auto") &&
+                // ... and for every width when the banded kernel (plain output only) has won this CSR's timed trial or is asked for
+                const int cls = sizeof(T) >= 8 ? 1 : 0;
+                const bool band_wins = M.pull_choice[cls] == 4 || M.pull_choice[cls] == 0 || !strcmp(opt_get("spmv", "auto"), "band");
+                const bool unfuse = a.epi && !a.epi->peer && !a.mask && !a.epi->has_mask && (sizeof(T) >= 8 || band_wins) &&
+                                    (!strcmp(opt_get("spmv", "auto"), "auto") || !strcmp(opt_get("spmv", "auto"), "band")) &&
                                     A->nvals >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_unfuse_wide", 1) != 0;
+                const int native = (!sr.reads_a() || av == (const void *)M.val) ? A->type : -1;
                 if (a.epi && !unfuse) {
                     epi.active = 1;
                     epi.c_vals = (const T *)a.epi->c_vals; epi.c_present = a.epi->c_present; epi.mask = a.epi->mask;
@@ -641,7 +668,7 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
                     if (a.fused) *a.fused = true;
                 }
                 info = run_pull<SRT, T>(sr, M, mrows, A->nvals, (const T *)av, (const T *)uv, u->n, up, kflip, a.mask,
-                                        a.mask_comp, (T *)a.t_vals, a.t_present, epi, a.err);
+                                        a.mask_comp, (T *)a.t_vals, a.t_present, epi, a.err, native);
             }
         }
         dev_free(atmp);

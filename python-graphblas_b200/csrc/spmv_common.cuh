@@ -97,6 +97,48 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
 }
 
 
+// 128-bit loads straight into registers (no local staging array): WORDS 32-bit words from a 4*WORDS-aligned address
+template <int WORDS> __device__ __forceinline__ void load_words(unsigned (&w)[WORDS], const void *src) {
+    if constexpr (WORDS == 8) {
+        const uint4 v0 = reinterpret_cast<const uint4 *>(src)[0], v1 = reinterpret_cast<const uint4 *>(src)[1];
+        w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+    } else if constexpr (WORDS == 4) {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(src);
+        w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+    } else {
+        static_assert(WORDS == 2, "unsupported vector width");
+        const uint2 v0 = *reinterpret_cast<const uint2 *>(src);
+        w[0] = v0.x; w[1] = v0.y;
+    }
+}
+// element j of a packed run of T held in 32-bit words
+template <typename T, int WORDS> __device__ __forceinline__ T word_elem(const unsigned (&w)[WORDS], int j) {
+    T v;
+    if constexpr (sizeof(T) == 8) {
+        const unsigned long long u = (unsigned long long)w[2 * j] | ((unsigned long long)w[2 * j + 1] << 32);
+        memcpy(&v, &u, 8);
+    } else if constexpr (sizeof(T) == 4) {
+        const unsigned u = w[j];
+        memcpy(&v, &u, 4);
+    } else if constexpr (sizeof(T) == 2) {
+        const uint16_t u = (uint16_t)(w[j >> 1] >> (16 * (j & 1)));
+        memcpy(&v, &u, 2);
+    } else {
+        const uint8_t u = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        memcpy(&v, &u, 1);
+    }
+    return v;
+}
+
+template <typename SR, typename T> __device__ __forceinline__ void pv_combine(const SR &sr, T av, int ah, T &bv, int &bh) {
+    // (bv, bh) <- (av, ah) (+) (bv, bh): the earlier partial on the left
+    if (ah) {
+        bv = bh ? sr.add(av, bv) : av;
+        bh = 1;
+    }
+}
+
+
 // segmented pull SpMV (spmv_seg.cu).  Returns GrB_SUCCESS with *handled = false when the inputs do not fit the kernel
 // (unaligned arrays); the caller then falls back to the merge-path kernel.  `epi` may be null (plain T output).
 // hot_mode: -1 = follow option spmv_hot ("1" forces the hot-column cache), 0 = plain, 1 = hot-column cache when it is viable;
@@ -104,3 +146,9 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
 GrB_Info spmv_seg_run(int type_code, int add_op, int mul_op, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz,
                       const void *avals, const void *x, const uint8_t *xp, void *t_vals, uint8_t *t_present,
                       const void *epi_typed, std::string *err, bool *handled, int hot_mode, bool *used_hot);
+
+// column-banded pull SpMV (spmv_band.cu): x staged one 128 KB column window at a time in shared memory.  *handled = false when the
+// format does not apply (values would need a typecast, tiny matrix); plain T output only (no fused write-back).
+GrB_Info spmv_band_run(int type_code, int add_op, int mul_op, CsrArrays &M, int64_t mrows, int64_t ncols, int64_t nnz, int val_type,
+                       const void *x, const uint8_t *xp, void *t_vals, uint8_t *t_present, std::string *err, bool *handled);
+void csr_drop_band(CsrArrays &c);

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "grb_ops.cuh"
+void csr_drop_band(CsrArrays &c);   // spmv_band.cu
 
 // ------------------------------------------------------------------ sortedness check
 __global__ void check_sorted_kernel(int64_t nrows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
@@ -265,6 +266,7 @@ GrB_Info matrix_ensure_sorted(GrB_Matrix A) {
     }
     if (!info) A->jumbled = false;
     csr_drop_hot(A->csr);   // positions of the column indices moved
+    csr_drop_band(A->csr);
     return info;
 }
 

@@ -122,6 +122,59 @@ def matrix_export_host_csr32(A, indptr, col_indices, values, *, sort=False):
           GrB_Index(col_indices.shape[0] if col_indices is not None else A.nvals), A, 1 if sort else 0])
 
 
+def matrix_export_host_csr32_async(A, indptr, col_indices, values):
+    """enqueue the D2H copies of A's CSR on the library's copy stream (they overlap later computation); the arrays must be
+    pinned and, like A, stay alive until copy_sync()"""
+    call("GrB_cuda_Matrix_export_csr32_async",
+         [ctypes.c_void_p(indptr.ctypes.data) if indptr is not None else None,
+          ctypes.c_void_p(col_indices.ctypes.data) if col_indices is not None else None,
+          ctypes.c_void_p(values.ctypes.data) if values is not None else None,
+          GrB_Index(col_indices.shape[0] if col_indices is not None else A.nvals), A])
+
+
+def copy_sync():
+    call("GrB_cuda_copy_sync", [])
+
+
+def mxm_to_host_csr32(A, B, semiring, out_indptr, out_cols, out_vals, *, blocks=8):
+    """C = A (+).(x) B straight into host CSR arrays (pinned numpy views: int64 / int32 / values), formed in `blocks` row
+    blocks of A with (nearly) equal entry counts: block k leaves the device over PCIe while block k + 1 is being multiplied,
+    so the call takes about max(D2H time, multiply time) instead of their sum.  Rows come out unsorted ("jumbled"), like
+    every mxm result before it is sorted on demand.  Returns nvals(C)."""
+    import torch
+
+    ip, cj, cx = matrix_as_torch(A, sync=False)
+    m, n = A.nrows, A.ncols
+    nnz = int(ip[-1])
+    targets = torch.tensor([nnz * k // blocks for k in range(blocks + 1)], dtype=torch.int64, device=ip.device)
+    bounds = torch.searchsorted(ip, targets).tolist()
+    bounds[0], bounds[-1] = 0, m
+    for k in range(1, len(bounds)):
+        bounds[k] = max(bounds[k], bounds[k - 1])
+    keep, offs = [], []
+    off = 0
+    for q0, q1 in zip(bounds[:-1], bounds[1:]):
+        if q1 == q0:
+            continue
+        k0, k1 = int(ip[q0]), int(ip[q1])
+        Ab = matrix_from_device_csr((ip[q0:q1 + 1] - k0).contiguous(), cj[k0:k1], cx[k0:k1], q1 - q0, n)
+        Cb = Ab.mxm(B, semiring).new()
+        nv = Cb.nvals
+        if off + nv > out_cols.shape[0]:
+            copy_sync()
+            raise ValueError(f"output arrays too small: need more than {out_cols.shape[0]} entries")
+        matrix_export_host_csr32_async(Cb, out_indptr[q0:q1 + 1], out_cols[off:off + nv], out_vals[off:off + nv])
+        keep.append(Cb)
+        offs.append((q0, q1, off))
+        off += nv
+    copy_sync()
+    for q0, q1, o in offs:   # block-local row pointers -> global ones
+        if o:
+            out_indptr[q0:q1] += o
+    out_indptr[m] = off
+    return off
+
+
 def _torch_dtype(dt):
     import torch
 

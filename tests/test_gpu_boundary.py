@@ -235,3 +235,30 @@ def test_whole_object_assign_and_setelement(gb):
     assert C.nvals == k0 + 1 and C[free].new() == 5
     with pytest.raises(gb.exceptions.InvalidIndex):
         call("GrB_Matrix_setElement_INT64", [C, ctypes.c_int64(1), GrB_Index(9), GrB_Index(0)])
+
+
+def test_scipy_and_matrix_market_converters(gb, tmp_path):
+    """graphblas_b200.io (reference graphblas/io/_scipy.py:8-119, io/_matrixmarket.py:8-140): scipy.sparse in every layout,
+    duplicate coordinates with dup_op, Matrix Market round trip, a Vector as an n x 1 array"""
+    import scipy.sparse as ss
+
+    rng = np.random.default_rng(12)
+    S_ = ss.random(60, 45, density=0.1, format="csr", random_state=3, dtype=np.float64)
+    S_.data = np.round(S_.data * 10) + 1
+    for fmt in ("csr", "csc", "coo", "lil"):
+        A = gb.io.from_scipy_sparse(S_.asformat(fmt))
+        back = gb.io.to_scipy_sparse(A, "csr")
+        assert (back != S_).nnz == 0 and back.shape == S_.shape and A.dtype == gb.dtypes.FP64
+    assert (gb.io.to_scipy_sparse(A, "csc") != S_.tocsc()).nnz == 0
+    dup = ss.coo_array((np.array([1, 2, 5]), (np.array([0, 0, 1]), np.array([1, 1, 0]))), shape=(2, 2))
+    with pytest.raises(ValueError, match="Duplicate indices found"):
+        gb.io.from_scipy_sparse(dup)
+    assert gb.io.from_scipy_sparse(dup, dup_op=gb.binary.plus).to_coo()[2].tolist() == [3, 5]
+    assert gb.io.from_scipy_sparse(ss.csr_array((4, 7), dtype=np.int32)).nvals == 0
+    path = str(tmp_path / "m.mtx")
+    gb.io.mmwrite(path, A)
+    B = gb.io.mmread(path)
+    assert B.isequal(A)
+    v = gb.Vector.from_coo([1, 4], [2.5, -1.0], size=6)
+    col = gb.io.to_scipy_sparse(v)
+    assert col.shape == (6, 1) and col[4, 0] == -1.0 and col.nnz == 2

