@@ -320,6 +320,9 @@ GrB_Info GrB_cuda_Vector_import_dense(GrB_Vector *v, GrB_Type type, GrB_Index n,
 GrB_Info GrB_cuda_Vector_export_dense(void *vals, uint8_t *present, const GrB_Vector v);
 GrB_Info GrB_cuda_Vector_touch(GrB_Vector v); /* arrays were modified through device_arrays(): drop caches */
 GrB_Info GrB_cuda_Matrix_sort(GrB_Matrix A);          /* finish a lazily "jumbled" result now */
+/* squeeze a row-end product (rows in order, unused slots between them: how GrB_mxm leaves a result that hardly compresses)
+   into the compact CSR now; a no-op on a compact matrix.  GrB_Matrix_wait(A, GrB_MATERIALIZE) does this and the sort. */
+GrB_Info GrB_cuda_Matrix_compact(GrB_Matrix A);
 GrB_Info GrB_cuda_Matrix_build_transpose(GrB_Matrix A); /* prebuild + cache the CSR of A' */
 /* mxm symbolic phase only: *flops, *nvals_out of A(+).(x)B without forming it */
 GrB_Info GrB_cuda_mxm_symbolic(GrB_Index *flops, GrB_Index *nvals_out, const GrB_Matrix A, const GrB_Matrix B,

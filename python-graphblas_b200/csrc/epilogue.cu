@@ -169,6 +169,7 @@ GrB_Info matrix_write_back(GrB_Matrix C, GrB_Matrix T, const GrB_Matrix M, const
     if (accum && accum->type != C->type)
         return set_error(&C->err, GrB_NOT_IMPLEMENTED, "accumulator %s must be typed like the output (%s)", accum->name,
                          type_of_code(C->type)->name);
+    if (T->csr.end && (T->type != C->type || M || accum || comp)) GRB_TRY(matrix_materialize(T));
     if (T->type != C->type && T->nvals > 0) {
         void *cast = dev_alloc((size_t)T->nvals * type_size(C->type));
         if (!cast) return set_error(&C->err, GrB_OUT_OF_MEMORY, "typecast of result");

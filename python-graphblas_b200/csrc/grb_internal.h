@@ -49,6 +49,13 @@ struct CsrArrays {
     int64_t *ptr = nullptr;   // nrows+1
     int32_t *idx = nullptr;   // nvals
     void *val = nullptr;      // nvals * type_size
+    // "row-end" form (an mxm result before anything needs it compact): row i occupies [ptr[i], end[i]) of idx / val, which hold
+    // `cap` slots; ptr is monotone (rows stay in row order) but ptr[i + 1] - end[i] slots may be unused.  This is the 4-array CSR of
+    // the sparse BLAS (pointerB / pointerE); the multiply kernels read it as it is (they take a row-end pointer: ptr + 1 for a
+    // compact CSR), everything else first calls matrix_materialize(), which squeezes the gaps out once.  nullptr: compact.
+    int64_t *end = nullptr;
+    int64_t *canon = nullptr; // nrows+1 compact row pointers of a row-end CSR (kept from the count scan, so compaction is one kernel)
+    int64_t cap = 0;
     int64_t *tile_starts = nullptr;  // merge-path tile row coordinates (cached; see spmv.cu)
     int64_t n_tiles = 0;
     int tile_items = 0;
@@ -126,6 +133,7 @@ void *dev_alloc(size_t bytes);             // stream-ordered; returns nullptr on
 void dev_free(void *p);
 void *ws_acquire(int slot, size_t bytes);   // cached scratch (see runtime.cu)
 void ws_release(int slot, void *p);
+void ws_detach(int slot, void *p);          // the caller keeps the block (it leaves the cache; free it with dev_free)
 void ws_trim();
 template <typename T> static inline T *dev_alloc_t(size_t n) { return (T *)dev_alloc(n * sizeof(T)); }
 const char *opt_get(const char *key, const char *dflt);
@@ -161,7 +169,11 @@ void matrix_take(GrB_Matrix dst, GrB_Matrix src);  // move arrays of src into ds
 GrB_Info matrix_ensure_sorted(GrB_Matrix A);       // sort.cu
 GrB_Info matrix_ensure_twin(GrB_Matrix A);         // transpose.cu
 GrB_Info matrix_new_shell(GrB_Matrix *A, int type, int64_t nrows, int64_t ncols);
-GrB_Info matrix_materialize(GrB_Matrix A);         // make sure csr.ptr exists (all-zero for an empty matrix)
+GrB_Info matrix_materialize(GrB_Matrix A);         // make sure csr.ptr exists (all-zero for an empty matrix) and the CSR is compact
+GrB_Info matrix_ensure_ptr(GrB_Matrix A);          // csr.ptr exists; a row-end CSR is left as it is (multiply operands)
+GrB_Info csr_compact(GrB_Matrix A);                // row-end CSR -> compact CSR (spgemm.cu)
+static inline const int64_t *csr_row_end(const CsrArrays &c) { return c.end ? c.end : c.ptr + 1; }
+static inline int64_t csr_slots(const CsrArrays &c, int64_t nvals) { return c.end ? c.cap : nvals; }
 GrB_Info vector_ensure_arrays(GrB_Vector v);       // allocate vals/present (present zeroed) if missing
 GrB_Info vector_count(GrB_Vector v);               // make nvals known
 void vector_release(GrB_Vector v);

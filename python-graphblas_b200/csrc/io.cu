@@ -391,6 +391,7 @@ extern "C" GrB_Info GrB_cuda_Matrix_extractElement(void *x, GrB_Type xtype, cons
     if (!valid(A)) return GrB_UNINITIALIZED_OBJECT;
     if (i >= (GrB_Index)A->nrows || j >= (GrB_Index)A->ncols) return set_error(&A->err, GrB_INVALID_INDEX, "extractElement: index out of range");
     if (!A->csr.ptr || A->nvals == 0) return GrB_NO_VALUE;
+    GRB_TRY(matrix_materialize(A));
     int64_t be[2];
     cudaMemcpyAsync(be, A->csr.ptr + i, 16, cudaMemcpyDeviceToHost, g_stream);
     cudaStreamSynchronize(g_stream);

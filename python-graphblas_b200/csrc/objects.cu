@@ -65,6 +65,8 @@ void csr_free(CsrArrays &c) {
     dev_free(c.ptr);
     dev_free(c.idx);
     dev_free(c.val);
+    dev_free(c.end);
+    dev_free(c.canon);
     dev_free(c.tile_starts);
     csr_drop_hot(c);
     csr_drop_seg(c);
@@ -112,12 +114,16 @@ GrB_Info matrix_alloc_csr(GrB_Matrix A, int64_t nvals) {
 }
 
 // an empty matrix still needs a valid (all-zero) row pointer array for kernels
-static GrB_Info matrix_ensure_ptr(GrB_Matrix A) {
+GrB_Info matrix_ensure_ptr(GrB_Matrix A) {
     if (A->csr.ptr) return GrB_SUCCESS;
     GRB_TRY(matrix_alloc_csr(A, 0));
     return fill_bytes(A->csr.ptr, 0, sizeof(int64_t) * ((size_t)A->nrows + 1));
 }
-GrB_Info matrix_materialize(GrB_Matrix A) { return matrix_ensure_ptr(A); }
+GrB_Info matrix_materialize(GrB_Matrix A) {
+    GRB_TRY(matrix_ensure_ptr(A));
+    if (A->csr.end) GRB_TRY(csr_compact(A));
+    return GrB_SUCCESS;
+}
 
 void matrix_take(GrB_Matrix dst, GrB_Matrix src) {
     csr_free(dst->csr);
@@ -179,7 +185,8 @@ extern "C" GrB_Info GrB_Matrix_dup(GrB_Matrix *C, const GrB_Matrix A) {
     GrB_Matrix M;
     GRB_TRY(matrix_new_shell(&M, A->type, A->nrows, A->ncols));
     if (A->csr.ptr) {
-        GrB_Info info = csr_copy(M->csr, A->csr, A->nrows, A->nvals, A->type, &A->err);
+        GrB_Info info = matrix_materialize(A);
+        if (!info) info = csr_copy(M->csr, A->csr, A->nrows, A->nvals, A->type, &A->err);
         if (info) { delete M; return info; }
         M->nvals = A->nvals;
         M->jumbled = A->jumbled;
@@ -213,7 +220,10 @@ extern "C" GrB_Info GrB_Matrix_nvals(GrB_Index *n, const GrB_Matrix A) {
 }
 extern "C" GrB_Info GrB_Matrix_wait(GrB_Matrix A, GrB_WaitMode mode) {
     if (!valid(A)) return GrB_UNINITIALIZED_OBJECT;
-    if (mode == GrB_MATERIALIZE) GRB_TRY(matrix_ensure_sorted(A));
+    if (mode == GrB_MATERIALIZE) {   // finish everything the object still owes: compact row-end storage, sorted rows
+        GRB_TRY(matrix_materialize(A));
+        GRB_TRY(matrix_ensure_sorted(A));
+    }
     CUDA_TRY(&A->err, cudaStreamSynchronize(g_stream));
     return GrB_SUCCESS;
 }

@@ -236,6 +236,10 @@ void ws_release(int slot, void *p) {
     if (p && p == w.ptr) { w.busy = false; return; }
     dev_free(p);
 }
+void ws_detach(int slot, void *p) {
+    auto &w = g_ws[slot];
+    if (p && p == w.ptr) { w.ptr = nullptr; w.bytes = 0; w.busy = false; }
+}
 void ws_trim() {
     for (auto &w : g_ws)
         if (w.ptr && !w.busy) { dev_free(w.ptr); w.ptr = nullptr; w.bytes = 0; }

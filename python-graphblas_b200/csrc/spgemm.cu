@@ -40,6 +40,12 @@ __device__ __forceinline__ int table_size_for(int64_t cnt, int cap, int tf8) {
     if (s < 32) s = 32;
     return (int)(s > cap ? cap : s);
 }
+// heavy rows are split over several CTAs by a second, independent hash of the column (spgemm_block_kernel, `part_offs`)
+__device__ __forceinline__ int part_of_key(int key, int parts) {
+    return (int)(((unsigned long long)((unsigned)key * 0x85EBCA6Bu) * (unsigned)parts) >> 32);
+}
+// parts of a row with flop bound c when a part's table holds `maxc` keys: 1/8 head-room for the imbalance of the split
+__host__ __device__ __forceinline__ int64_t parts_of(int64_t c, int64_t maxc) { return (c + (c >> 3) + maxc - 1) / maxc; }
 template <typename T> struct Packed { static constexpr bool value = sizeof(T) <= 4; };
 template <typename T> __device__ __forceinline__ unsigned long long pack_entry(int key, T v) {
     unsigned int bits = 0;
@@ -86,7 +92,8 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
             if (cas_first) {   // most products of a low-compression row open a new slot: one atomic, no probe load
                 // (looking first with a plain load on the later probes and spending the atomic only on an empty slot was measured
                 //  slower: 41.1 vs 36.9 ms for the CTA-per-row bins of the scale-22 product -- the extra LDS lengthens the chain)
-                while (true) {
+                unsigned budget = size;   // a full table would probe for ever: trap instead (tables are sized from an upper bound,
+                while (true) {            // a split row's part from an expectation with head-room -- this is the safety net)
                     const unsigned long long cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
                     if (cur == HASH_EMPTY64) return 1;
                     if ((int)(cur >> 32) == j) {
@@ -94,6 +101,7 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
                         return 0;
                     }
                     h = (h + 1 == size) ? 0 : h + 1;
+                    if (--budget == 0) __trap();
                 }
             }
             while (true) {
@@ -109,6 +117,7 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
                 h = (h + 1 == size) ? 0 : h + 1;
             }
         } else {
+            unsigned budget = size;
             while (true) {
                 int cur = keys[h];
                 int fresh = 0;
@@ -121,6 +130,7 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
                     return fresh;
                 }
                 h = (h + 1 == size) ? 0 : h + 1;
+                if (--budget == 0) __trap();
             }
         }
     }
@@ -223,8 +233,9 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
 };
 
 // ------------------------------------------------------------------ flops per row
-__global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj,
-                                 const int64_t *__restrict__ Bp, int64_t *__restrict__ flops) {
+// (row-end pointers: Ae[i] is where row i stops -- Ap + 1 for a compact CSR, the end array of a row-end CSR; Be likewise)
+__global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, const int64_t *__restrict__ Ae, const int32_t *__restrict__ Aj,
+                                 const int64_t *__restrict__ Bp, const int64_t *__restrict__ Be, int64_t *__restrict__ flops) {
     // 8 lanes per row, 4 rows per warp per step; the whole warp runs the same trip count (shuffles inside)
     const int lane = threadIdx.x & 7, sub = (threadIdx.x & 31) >> 3;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -233,9 +244,9 @@ __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, 
         const int64_t i = base + sub;
         int64_t f = 0;
         if (i < nrows)
-            for (int64_t k = Ap[i] + lane; k < Ap[i + 1]; k += 8) {
+            for (int64_t k = Ap[i] + lane; k < Ae[i]; k += 8) {
                 int32_t r = Aj[k];
-                f += Bp[r + 1] - Bp[r];
+                f += Be[r] - Bp[r];
             }
         f += __shfl_down_sync(0xffffffffu, f, 4, 8);
         f += __shfl_down_sync(0xffffffffu, f, 2, 8);
@@ -292,11 +303,12 @@ __device__ __forceinline__ int bin_of(const BinSpec &s, int64_t c) {
 }
 __host__ __device__ __forceinline__ int64_t gtable_size_of(int64_t c) { return (2 * c + 1024) & ~(int64_t)3; }   // multiple of 4 keeps the value array 16-byte aligned
 // bin_counts[0..NBINS) = rows per bin; bin_counts[NBINS] = total global-table entries the rows of the last bin need
+// bin_counts[NBINS + 1] = CTAs the rows of the last bin need when each is split into parts that fit the largest shared table
 __global__ void bin_count_kernel(BinSpec spec, int64_t nrows, const int64_t *__restrict__ cnt, unsigned long long *__restrict__ bin_counts) {
     __shared__ unsigned int s[NBINS];
-    __shared__ unsigned long long s_g;
+    __shared__ unsigned long long s_g, s_p;
     if (threadIdx.x < NBINS) s[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_g = 0;
+    if (threadIdx.x == 0) { s_g = 0; s_p = 0; }
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -304,11 +316,14 @@ __global__ void bin_count_kernel(BinSpec spec, int64_t nrows, const int64_t *__r
         const int64_t c = cnt[i];
         const int b = bin_of(spec, c);
         atomicAdd(&s[b], 1u);
-        if (b == NBINS - 1) atomicAdd(&s_g, (unsigned long long)gtable_size_of(c));
+        if (b == NBINS - 1) {
+            atomicAdd(&s_g, (unsigned long long)gtable_size_of(c));
+            atomicAdd(&s_p, (unsigned long long)parts_of(c, spec.maxcount[BIN_LAST_SHARED]));
+        }
     }
     __syncthreads();
     if (threadIdx.x < NBINS && s[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], (unsigned long long)s[threadIdx.x]);
-    if (threadIdx.x == 0 && s_g) atomicAdd(&bin_counts[NBINS], s_g);
+    if (threadIdx.x == 0 && s_g) { atomicAdd(&bin_counts[NBINS], s_g); atomicAdd(&bin_counts[NBINS + 1], s_p); }
 }
 struct BinCursors { unsigned long long v[NBINS]; };
 __global__ void bin_cursors_kernel(BinCursors c, unsigned long long *__restrict__ cursors) {
@@ -346,8 +361,8 @@ struct MaskArgs { const int64_t *Mp; const int32_t *Mj; const uint8_t *Meff; int
 template <typename SR, typename T, bool NUMERIC, bool PACK>
 __global__ void __launch_bounds__(256)
 spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
-                   const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
-                   const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                   const int64_t *__restrict__ Ap, const int64_t *__restrict__ Ae, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                   const int64_t *__restrict__ Bp, const int64_t *__restrict__ Be, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
                    int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj, T *__restrict__ Ox,
                    MaskArgs mk) {
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
@@ -373,12 +388,12 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
     int local_new = 0;
     if (active) {
         const int sub = lane32 / LPE, lane = lane32 % LPE;
-        const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
+        const int64_t a_beg = Ap[row], a_end = Ae[row];
         for (int64_t k = a_beg + sub; k < a_end; k += 32 / LPE) {
             const int32_t br = Aj[k];
             T a = one_of<T>();
             if (NUMERIC && sr.reads_a()) a = Ax[k];
-            const int64_t b_beg = Bp[br], b_end = Bp[br + 1];
+            const int64_t b_beg = Bp[br], b_end = Be[br];
             for (int64_t q = b_beg + lane; q < b_end; q += LPE) {
                 const int j = Bj[q];
                 T p = T();
@@ -410,22 +425,44 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
 constexpr int UNROLL = 4;
 template <typename SR, typename T, bool NUMERIC, bool PACK, bool GLOBAL>
 __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, int flags, const int64_t *__restrict__ cnt,
-                                    const int64_t *__restrict__ Ap, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
-                                    const int64_t *__restrict__ Bp, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                                    const int64_t *__restrict__ Ap, const int64_t *__restrict__ Ae, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                                    const int64_t *__restrict__ Bp, const int64_t *__restrict__ Be, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
                                     int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
-                                    T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets, MaskArgs mk) {
+                                    T *__restrict__ Ox, unsigned char *g_table, const int64_t *__restrict__ g_offsets, MaskArgs mk,
+                                    const int64_t *__restrict__ part_offs, int n_split_rows, int64_t part_maxc) {
     typedef HashTable<SR, T, NUMERIC, PACK> Table;
     // dynamic shared memory: [hash table: cap entries (none when GLOBAL)] [s_bs: B-row starts] [s_off: product prefix] [s_av: A values]
     // -- the staging arrays are sized by blockDim, so a 128-thread CTA of a small bin costs 2 KB, not the 16 KB of 1024 threads
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_wsum[MAX_THREADS / 32];
-    __shared__ int s_count;
+    __shared__ int s_count, s_new;
+    __shared__ long long s_base;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const size_t tbytes = GLOBAL ? 0 : (((size_t)cap * Table::entry_bytes() + 15) & ~(size_t)15);
     int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + tbytes);
     int *s_off = reinterpret_cast<int *>(s_bs + nthreads);
     T *s_av = reinterpret_cast<T *>(s_off + ((nthreads + 4) & ~3));
-    const int64_t row = rows[blockIdx.x];
+    // SPLIT rows (part_offs != nullptr; unmasked, shared tables only): row rows[r] is hashed by part_offs[r + 1] - part_offs[r]
+    // CTAs; CTA `part` of a row reads ALL of the row's products (B rows are streamed from L2) but keeps only the columns whose
+    // part hash is `part`, so the pieces are disjoint, each fits a shared-memory table, and a heavy row no longer crawls through
+    // a global-memory table on one SM.  Every CTA reserves its piece of the row's output with one atomic on the row's counter
+    // (the order of a row's entries is free: results are "jumbled" anyway).
+    int parts = 1, part = 0;
+    int64_t row;
+    if (part_offs) {
+        int lo = 0, hi = n_split_rows - 1;
+        const int64_t me = blockIdx.x;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (part_offs[mid] <= me) lo = mid;
+            else hi = mid - 1;
+        }
+        row = rows[lo];
+        parts = (int)(part_offs[lo + 1] - part_offs[lo]);
+        part = (int)(me - part_offs[lo]);
+    } else {
+        row = rows[blockIdx.x];
+    }
 
     Table tab;
     if (GLOBAL) {   // global-memory table: [offset, offset + size) entries of this row
@@ -436,10 +473,12 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         unsigned char *vbase = g_table + (size_t)total * 4 + (size_t)off * sizeof(T);
         tab.bind(kbase, sz, vbase, flags & 1);
     } else {
-        tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4, flags & 1);
+        // a part expects 1 / parts of the row's keys; parts_of() left 1/8 head-room below part_maxc
+        const int64_t c_eff = parts > 1 ? part_maxc : cnt[row];
+        tab.bind(s_raw, (unsigned)table_size_for(c_eff, cap, tf8), s_raw + (size_t)cap * 4, flags & 1);
     }
     tab.init(sr, tid, nthreads);
-    if (tid == 0) s_count = 0;
+    if (tid == 0) { s_count = 0; s_new = 0; }
     if (mk.Mp) {
         __syncthreads();
         for (int64_t k = mk.Mp[row] + tid; k < mk.Mp[row + 1]; k += nthreads)
@@ -447,7 +486,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
     }
 
     const int wlane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const int64_t a_beg = Ap[row], a_end = Ap[row + 1];
+    const int64_t a_beg = Ap[row], a_end = Ae[row];
     int local_new = 0;
     for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
         const int chunk_n = (int)((a_end - c0 < nthreads) ? (a_end - c0) : nthreads);
@@ -456,7 +495,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
             const int64_t k = c0 + tid;
             const int32_t br = Aj[k];
             const int64_t bs = Bp[br];
-            len = (int)(Bp[br + 1] - bs);
+            len = (int)(Be[br] - bs);
             s_bs[tid] = bs;
             if (NUMERIC && sr.reads_a()) s_av[tid] = Ax[k];
         }
@@ -506,6 +545,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 if (jj[u] == HASH_EMPTY) continue;
+                if (parts > 1 && part_of_key(jj[u], parts) != part) continue;
                 T pr = T();
                 if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
                 local_new += mk.Mp ? (mk.comp ? tab.insert_comp(sr, jj[u], pr) : tab.accumulate_masked(sr, jj[u], pr)) : tab.insert(sr, jj[u], pr);
@@ -515,6 +555,18 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_new += __shfl_down_sync(0xffffffffu, local_new, o);
+    if (parts > 1) {
+        // this CTA's piece: its size is the number of keys it opened; one atomic on the row's counter places it
+        if (wlane == 0 && local_new) atomicAdd(&s_new, local_new);
+        __syncthreads();
+        if (tid == 0) s_base = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(&row_nnz[row]), (unsigned long long)s_new);
+        __syncthreads();
+        if (NUMERIC) {
+            const int64_t ob = Op[row] + s_base;
+            tab.drain(tid, nthreads, &s_count, Oj + ob, Ox + ob);
+        }
+        return;
+    }
     if (NUMERIC) {
         const int64_t ob = Op[row];
         tab.drain(tid, nthreads, &s_count, Oj + ob, Ox + ob);
@@ -527,6 +579,14 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         __syncthreads();
         if (tid == 0) row_nnz[row] = s_count;
     }
+}
+
+// parts per listed row (sizes[n]: pad slot of the in-place exclusive scan)
+__global__ void split_parts_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt, int64_t maxc,
+                                   int64_t *__restrict__ sizes) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    sizes[i] = i < n ? parts_of(cnt[rows[i]], maxc) : 0;
 }
 
 __global__ void gtable_sizes_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt,
@@ -629,22 +689,23 @@ struct Bins {
     unsigned long long count[NBINS];   // rows per bin
     unsigned long long start[NBINS];   // offset of each bin inside rows[]
     unsigned long long gtable_entries = 0;   // global-table entries the rows of the last bin need in total
+    unsigned long long split_parts = 0;      // CTAs of the last bin when its rows are split into shared-table sized parts
     BinSpec spec;
 };
 
 static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const int64_t *cnt, std::string *err) {
     bins->spec = make_bin_spec(entry_bytes);
-    unsigned long long *d = dev_alloc_t<unsigned long long>(2 * NBINS + 2);
+    unsigned long long *d = dev_alloc_t<unsigned long long>(2 * NBINS + 3);   // counts[NBINS], global-table entries, split parts, cursors[NBINS]
     bins->rows = dev_alloc_t<int32_t>((size_t)(nrows > 0 ? nrows : 1));
     if (!d || !bins->rows) { dev_free(d); dev_free(bins->rows); bins->rows = nullptr; return set_error(err, GrB_OUT_OF_MEMORY, "spgemm bins"); }
-    cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (2 * NBINS + 2), g_stream);
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (2 * NBINS + 3), g_stream);
     int blocks = (int)std::min<int64_t>((nrows + 255) / 256 + 1, (int64_t)g_num_sms * 8);
     {
         LAUNCH_NOTE("spgemm_bin_count");
         bin_count_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d);
     }
-    unsigned long long hcount[NBINS + 1];
-    cudaMemcpyAsync(hcount, d, sizeof(unsigned long long) * (NBINS + 1), cudaMemcpyDeviceToHost, g_stream);
+    unsigned long long hcount[NBINS + 2];
+    cudaMemcpyAsync(hcount, d, sizeof(unsigned long long) * (NBINS + 2), cudaMemcpyDeviceToHost, g_stream);
     cudaStreamSynchronize(g_stream);   // the ONE host round trip of the binning: grid sizes of the per-bin launches
     BinCursors cur;
     unsigned long long off = 0;
@@ -655,10 +716,11 @@ static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const i
         if (b > 0) off += bins->count[b];
     }
     bins->gtable_entries = hcount[NBINS];
+    bins->split_parts = hcount[NBINS + 1];
     {
         LAUNCH_NOTE("spgemm_bin_fill");
-        bin_cursors_kernel<<<1, 32, 0, g_stream>>>(cur, d + NBINS + 1);   // cursors by value: no host buffer to keep alive, no sync
-        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d + NBINS + 1, bins->rows);
+        bin_cursors_kernel<<<1, 32, 0, g_stream>>>(cur, d + NBINS + 2);   // cursors by value: no host buffer to keep alive, no sync
+        bin_fill_kernel<<<blocks, 256, 0, g_stream>>>(bins->spec, nrows, cnt, d + NBINS + 2, bins->rows);
     }
     cudaError_t e = cudaGetLastError();
     dev_free(d);
@@ -667,8 +729,8 @@ static GrB_Info make_bins(Bins *bins, size_t entry_bytes, int64_t nrows, const i
 }
 
 struct HashArgs {
-    const int64_t *Ap; const int32_t *Aj; const void *Ax;
-    const int64_t *Bp; const int32_t *Bj; const void *Bx;
+    const int64_t *Ap; const int64_t *Ae; const int32_t *Aj; const void *Ax;   // Ae / Be: row-end pointers (csr_row_end)
+    const int64_t *Bp; const int64_t *Be; const int32_t *Bj; const void *Bx;
     int64_t *row_nnz;                  // written when non-null (symbolic count, or exact count of a one-pass row)
     const int64_t *Op; int32_t *Oj; void *Ox;   // numeric output: row i's entries go to O*[Op[i] ...]
     const int64_t *cnt;                // per-row bound the bins / table sizes were derived from
@@ -714,16 +776,38 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             auto kern = spgemm_warp_kernel<SR, T, NUMERIC, PACK>;
             if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
-            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
+            kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
         } else if (b < NBINS - 1) {
             const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
             CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_block" : "spgemm_symbolic_block");
-            kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk);
+            kern<<<(unsigned)n, threads, smem, st>>>(sr, rows, cap, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk, nullptr, 0, 0);
         } else {
             // rows whose bound exceeds the largest shared table: global-memory tables.  The total table size came back with the
             // bin counts, so the usual case is fully asynchronous: sizes -> device scan -> one launch, no host round trip
+            // unmasked products with exact-count output (row_nnz): split every such row over several CTAs with shared tables
+            const int64_t maxc = bins.spec.maxcount[BIN_LAST_SHARED];
+            if (!a.mk.Mp && a.row_nnz && bins.split_parts > 0 && bins.split_parts < ((unsigned long long)1 << 31) && n < ((int64_t)1 << 31) &&
+                opt_get_int("spgemm_split", 1) != 0) {
+                int64_t *poffs = dev_alloc_t<int64_t>((size_t)n + 1);
+                if (!poffs) return set_error(err, GrB_OUT_OF_MEMORY, "split row offsets");
+                note_launch("split_parts");
+                split_parts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, g_stream>>>(rows, n, a.cnt, maxc, poffs);
+                GrB_Info sinfo = exclusive_scan_i64(poffs, n + 1, err);
+                if (!sinfo) {
+                    const int scap = bins.spec.cap[BIN_LAST_SHARED], sthreads = bins.spec.threads[BIN_LAST_SHARED];
+                    const size_t smem = (((size_t)scap * entry + 15) & ~(size_t)15) + block_stage_bytes(sthreads, sizeof(T));
+                    auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
+                    CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                    LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_split" : "spgemm_symbolic_split");
+                    kern<<<(unsigned)bins.split_parts, sthreads, smem, g_stream>>>(sr, rows, scap, bins.spec.tf8[BIN_LAST_SHARED], bins.spec.flags, a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk, poffs, (int)n, maxc);
+                    cudaError_t ge = cudaGetLastError();
+                    if (ge != cudaSuccess) sinfo = cuda_fail(err, ge, "split-row spgemm kernel");
+                }
+                dev_free(poffs);
+                return sinfo;
+            }
             const int64_t budget_entries = (int64_t)opt_get_int("spgemm_gtable_entries", (long)1 << 30);
             const int64_t tot_all = (int64_t)bins.gtable_entries;
             if (tot_all <= budget_entries) {
@@ -739,7 +823,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 }
                 if (!ginfo) {
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)n, 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)n, 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk, nullptr, 0, 0);
                     cudaError_t ge = cudaGetLastError();
                     if (ge != cudaSuccess) ginfo = cuda_fail(err, ge, "global-table spgemm kernel");
                 }
@@ -771,7 +855,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 if (!info) {
                     cudaMemcpyAsync(doffs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, g_stream);
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_global" : "spgemm_symbolic_global");
-                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows + i0, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Aj, (const T *)a.Ax, a.Bp, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk);
+                    spgemm_block_kernel<SR, T, NUMERIC, PACK, true><<<(unsigned)(i1 - i0), 1024, block_stage_bytes(1024, sizeof(T)), g_stream>>>(sr, rows + i0, 0, bins.spec.tf8[b], bins.spec.flags, a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, gt, doffs, a.mk, nullptr, 0, 0);
                     cudaStreamSynchronize(g_stream);   // offs is host memory
                 }
                 dev_free(doffs); dev_free(gt);
@@ -820,7 +904,7 @@ static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p,
         if (sr.reads_a()) info = cast_view(&ax, &atmp, p.A->val, p.a_type, T_code, p.annz, err);
         if (!info && sr.reads_b()) info = cast_view(&bx, &btmp, p.B->val, p.b_type, T_code, p.bnnz, err);
         if (!info) {
-            HashArgs a{p.A->ptr, p.A->idx, ax, p.B->ptr, p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt, mk};
+            HashArgs a{p.A->ptr, csr_row_end(*p.A), p.A->idx, ax, p.B->ptr, csr_row_end(*p.B), p.B->idx, bx, row_nnz, Op, Oj, Ox, cnt, mk};
             if (!info) {
                 if (Packed<T>::value && use_packed()) info = run_bins<SRT, T, true, true>(sr, bins, a, err);
                 else info = run_bins<SRT, T, true, false>(sr, bins, a, err);
@@ -832,6 +916,17 @@ static GrB_Info spgemm_numeric_typed(const GrB_Semiring op, const SpgemmPlan &p,
     return info;
 }
 
+__global__ void row_end_kernel(int64_t nrows, const int64_t *__restrict__ Sp, int64_t *__restrict__ cnt_to_end) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= nrows; i += s) cnt_to_end[i] = Sp[i] + (i < nrows ? cnt_to_end[i] : 0);
+}
+__global__ void row_len_kernel(int64_t nrows, const int64_t *__restrict__ beg, const int64_t *__restrict__ end, int64_t *__restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= nrows; i += s) len[i] = i < nrows ? end[i] - beg[i] : 0;
+}
+
 template <typename T>
 static void launch_compact(int64_t m, const int64_t *Sp, const int64_t *Cp, const int32_t *Sj, const void *Sx, int32_t *Cj, void *Cx) {
     int blocks = (int)std::min<int64_t>((m + 7) / 8, (int64_t)g_num_sms * 32);
@@ -839,6 +934,42 @@ static void launch_compact(int64_t m, const int64_t *Sp, const int64_t *Cp, cons
     compact_rows_kernel<T><<<blocks, 256, 0, g_stream>>>(m, Sp, Cp, Sj, (const T *)Sx, Cj, (T *)Cx);
 }
 
+
+// row-end CSR -> compact CSR, once, for consumers that walk ptr[i] .. ptr[i + 1] (matrix_materialize)
+GrB_Info csr_compact(GrB_Matrix A) {
+    CsrArrays &c = A->csr;
+    if (!c.end) return GrB_SUCCESS;
+    const int64_t m = A->nrows;
+    const size_t es = type_size(A->type);
+    std::string *err = &A->err;
+    if (!c.canon) {
+        c.canon = dev_alloc_t<int64_t>((size_t)m + 1);
+        if (!c.canon) return set_error(err, GrB_OUT_OF_MEMORY, "compaction row pointers");
+        note_launch("row_len");
+        row_len_kernel<<<(unsigned)std::min<int64_t>((m + 256) / 256, (int64_t)g_num_sms * 8), 256, 0, g_stream>>>(m, c.ptr, c.end, c.canon);
+        GRB_TRY(exclusive_scan_i64(c.canon, m + 1, err));
+    }
+    const size_t nv = (size_t)(A->nvals > 0 ? A->nvals : 1);
+    int32_t *nj = dev_alloc_t<int32_t>(nv);
+    void *nx = dev_alloc(nv * es);
+    if (!nj || !nx) {
+        dev_free(nj); dev_free(nx);
+        return set_error(err, GrB_OUT_OF_MEMORY, "compaction of a %lld-entry product needs %.1f GB more", (long long)A->nvals, (double)nv * (4 + es) / 1e9);
+    }
+    if (A->nvals > 0) {
+        switch (es) {
+            case 1: launch_compact<uint8_t>(m, c.ptr, c.canon, c.idx, c.val, nj, nx); break;
+            case 2: launch_compact<uint16_t>(m, c.ptr, c.canon, c.idx, c.val, nj, nx); break;
+            case 4: launch_compact<uint32_t>(m, c.ptr, c.canon, c.idx, c.val, nj, nx); break;
+            default: launch_compact<uint64_t>(m, c.ptr, c.canon, c.idx, c.val, nj, nx); break;
+        }
+        CUDA_TRY(err, cudaGetLastError());
+    }
+    dev_free(c.ptr); dev_free(c.end); dev_free(c.idx); dev_free(c.val);
+    c.ptr = c.canon; c.canon = nullptr; c.end = nullptr; c.cap = 0;
+    c.idx = nj; c.val = nx;
+    return GrB_SUCCESS;
+}
 
 // ------------------------------------------------------------------ tiled one-pass (spgemm_tile.cuh): host side
 struct TileCfg { bool on = false; int threads = 256, ctas = 2, tcap = 0, scap = 0, tf8 = 12; int64_t R = 0, W = 0; size_t smem = 0; };
@@ -1021,8 +1152,11 @@ static GrB_Info spgemm_tiled_typed(const GrB_Semiring op, const SpgemmPlan &p, c
 GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, GrB_Matrix B, bool bt, const GrB_Matrix M,
                 bool mask_comp, bool mask_struct, std::string *err, bool symbolic_only, uint64_t *flops_out,
                 uint64_t *nvals_out) {
-    GRB_TRY(matrix_materialize(A));
-    GRB_TRY(matrix_materialize(B));
+    // operands may be row-end CSRs (earlier products): the hash kernels read them as they are; only the tile kernel (bulk
+    // copies over the row pointer) and the transposed twins need the compact form
+    const bool want_tile = !symbolic_only && opt_get_int("spgemm_tile", 0) != 0;
+    GRB_TRY(want_tile ? matrix_materialize(A) : matrix_ensure_ptr(A));
+    GRB_TRY(want_tile ? matrix_materialize(B) : matrix_ensure_ptr(B));
     if (at) GRB_TRY(matrix_ensure_twin(A));
     if (bt) GRB_TRY(matrix_ensure_twin(B));
     SpgemmPlan p;
@@ -1032,7 +1166,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
     p.k = at ? A->nrows : A->ncols;
     const int64_t bk = bt ? B->ncols : B->nrows;
     p.n = bt ? B->nrows : B->ncols;
-    p.annz = A->nvals; p.bnnz = B->nvals;
+    p.annz = csr_slots(*p.A, A->nvals); p.bnnz = csr_slots(*p.B, B->nvals);   // value slots (a typecast copies all of them)
     p.a_type = A->type; p.b_type = B->type;
     if (p.k != bk)
         return set_error(err, GrB_DIMENSION_MISMATCH, "mxm: inner dimensions differ (%lld vs %lld)", (long long)p.k, (long long)bk);
@@ -1065,7 +1199,7 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
         int blocks = (int)std::min<int64_t>((p.m + 31) / 32, (int64_t)g_num_sms * 32);
         {
             LAUNCH_NOTE("spgemm_row_flops");
-            row_flops_kernel<<<blocks, 256, 0, g_stream>>>(p.m, p.A->ptr, p.A->idx, p.B->ptr, flops);
+            row_flops_kernel<<<blocks, 256, 0, g_stream>>>(p.m, p.A->ptr, csr_row_end(*p.A), p.A->idx, p.B->ptr, csr_row_end(*p.B), flops);
         }
         {
             LAUNCH_NOTE("reduce_sum_max");
@@ -1220,6 +1354,25 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             if (!info) total = read_i64(Tm->csr.ptr + p.m);
             phase_mark("mxm_numeric_wait");
         }
+        // A product that hardly compresses (nnz(C) within 1/8 of the flop bound: the R-MAT squares) stays where the hash
+        // kernels put it: the staging arrays BECOME the result as a row-end CSR (rows in row order, row i at [Sp[i], Sp[i] +
+        // count[i])), and nothing is copied.  Later multiplies read that form directly; anything that needs a compact CSR
+        // (export, sort, SpMV, element-wise ops) squeezes the gaps out once (matrix_materialize -> csr_compact).  Products that
+        // do compress are compacted here, because their staging would pin (flops - nnz) slots of memory for nothing.
+        if (!info && total > 0 && opt_get_int("spgemm_row_end", 1) != 0 && (uint64_t)total + total_flops / 8 >= total_flops) {
+            note_launch("row_end");
+            row_end_kernel<<<copy_blocks, 256, 0, g_stream>>>(p.m, Sp, row_nnz);
+            Tm->csr.canon = Tm->csr.ptr;
+            Tm->csr.ptr = Sp;
+            Tm->csr.end = row_nnz;
+            Tm->csr.idx = Sj;
+            Tm->csr.val = Sx;
+            Tm->csr.cap = (int64_t)total_flops;
+            ws_detach(0, Sj); ws_detach(1, Sx);   // the cached scratch blocks now belong to the matrix
+            Sp = nullptr; row_nnz = nullptr; Sj = nullptr; Sx = nullptr;
+            Tm->nvals = total;
+            Tm->jumbled = true;
+        } else {
         if (!info) {
             size_t nv = (size_t)(total > 0 ? total : 1);
             Tm->csr.idx = dev_alloc_t<int32_t>(nv);
@@ -1239,13 +1392,14 @@ GrB_Info spgemm(GrB_Matrix *Tout, const GrB_Semiring op, GrB_Matrix A, bool at, 
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) info = cuda_fail(err, e, "spgemm compaction");
         }
+        }
         dev_free(cmtmp);
     } else if (!info) {
         // ---- two-pass: symbolic count, exact allocation, numeric
         if (p.m > 0 && total_flops > 0) {
             info = make_bins(&fbins, 4, p.m, flops, err);
             if (!info) {
-                HashArgs a{p.A->ptr, p.A->idx, nullptr, p.B->ptr, p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops, MaskArgs{nullptr, nullptr, nullptr, 0}};
+                HashArgs a{p.A->ptr, csr_row_end(*p.A), p.A->idx, nullptr, p.B->ptr, csr_row_end(*p.B), p.B->idx, nullptr, row_nnz, nullptr, nullptr, nullptr, flops, MaskArgs{nullptr, nullptr, nullptr, 0}};
                 SRDyn<int32_t> dummy;
                 dummy.a_op = OP_ANY; dummy.m_op = OP_PAIR;
                 info = run_bins<SRDyn<int32_t>, int32_t, false, false>(dummy, fbins, a, err);

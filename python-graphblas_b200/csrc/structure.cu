@@ -255,6 +255,7 @@ template <typename V> static GrB_Info sort_rows_typed(GrB_Matrix A) {
 }
 
 GrB_Info matrix_ensure_sorted(GrB_Matrix A) {
+    if (A->csr.end) GRB_TRY(matrix_materialize(A));   // the sort kernels walk a compact CSR
     if (!A->jumbled || !A->csr.ptr || A->nvals == 0) { A->jumbled = false; return GrB_SUCCESS; }
     // the values are only moved, never interpreted: sort by byte width
     GrB_Info info;
@@ -270,6 +271,11 @@ GrB_Info matrix_ensure_sorted(GrB_Matrix A) {
     return info;
 }
 
+extern "C" GrB_Info GrB_cuda_Matrix_compact(GrB_Matrix A) {
+    if (!valid(A)) return GrB_UNINITIALIZED_OBJECT;
+    return matrix_materialize(A);
+}
+
 extern "C" GrB_Info GrB_cuda_Matrix_sort(GrB_Matrix A) {
     if (!valid(A)) return GrB_UNINITIALIZED_OBJECT;
     return matrix_ensure_sorted(A);
@@ -279,6 +285,7 @@ extern "C" GrB_Info GrB_cuda_Matrix_sort(GrB_Matrix A) {
 GrB_Info matrix_check_sorted(GrB_Matrix A, bool *sorted) {
     *sorted = true;
     if (!A->csr.ptr || A->nvals == 0) return GrB_SUCCESS;
+    GRB_TRY(matrix_materialize(A));
     int *flag = dev_alloc_t<int>(1);
     if (!flag) return GrB_OUT_OF_MEMORY;
     cudaMemsetAsync(flag, 0, 4, g_stream);

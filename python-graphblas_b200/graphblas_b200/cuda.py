@@ -288,6 +288,11 @@ def matrix_sort(A):
     call("GrB_cuda_Matrix_sort", [A])
 
 
+def matrix_compact(A):
+    """Squeeze a row-end product into the compact CSR now (export, sort, SpMV and element-wise ops do it on demand)."""
+    call("GrB_cuda_Matrix_compact", [A])
+
+
 def matrix_build_transpose(A):
     call("GrB_cuda_Matrix_build_transpose", [A])
 

@@ -351,6 +351,64 @@ def test_mxm_all_bins(gb):
     assert ok, msg
 
 
+@pytest.mark.parametrize("dtype,semiring", [(np.int64, "plus_times"), (np.float32, "plus_times"), (np.int32, "min_plus"), (np.float64, "plus_second")])
+def test_mxm_row_end_result_as_operand_and_through_consumers(gb, dtype, semiring):
+    """An unmasked product that hardly compresses is left as a row-end CSR (rows where the hash kernels put them, no compaction:
+    csrc/spgemm.cu).  The multiply kernels must read that form directly (as A, as B, as both), and every other consumer must
+    see the compact CSR: dup, extract tuples, element lookup, transpose, element-wise ops, reduce, mxv, wait(materialize).
+    Compared with the oracle's products; option spgemm_row_end=0 (eager compaction) must give the same matrices."""
+    rng = np.random.default_rng(abs(hash(("rowend", semiring, np.dtype(dtype).name))) % 2**32)
+    n = 700
+    r, c = H.random_coo(rng, n, n, 2600)          # ~3.7 per row: the square hardly compresses
+    v = H.random_values(rng, r.size, dtype)
+    A = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+    Ab = R.BigMat.from_coo(r, c, v, n, n)
+    sr = getattr(gb.semiring, semiring)
+    C2b = R.mxm_T(semiring, Ab, Ab)
+    assert C2b.nvals * 8 >= 7 * int(np.diff(Ab.indptr)[Ab.indices].sum()), "test matrix compresses too well to stay row-end"
+    for opt in (None, "0"):
+        gb.cuda.set_option("spgemm_row_end", opt)
+        try:
+            C2 = A.mxm(A, sr).new()
+            assert C2.nvals == C2b.nvals
+            left = C2.mxm(A, sr).new()            # row-end A operand
+            right = A.mxm(C2, sr).new()           # row-end B operand
+            both = C2.mxm(C2, sr).new()           # both
+            for got, want in ((left, R.mxm_T(semiring, C2b, Ab)), (right, R.mxm_T(semiring, Ab, C2b)), (both, R.mxm_T(semiring, C2b, C2b))):
+                ok, msg = H.mat_equal(got, want)
+                assert ok, (opt, msg)
+            D = A.mxm(A, sr).new()
+            ok, msg = H.mat_equal(D.dup(), C2b)   # dup of a row-end matrix
+            assert ok, msg
+            D = A.mxm(A, sr).new()
+            I, J, X = C2b.to_coo()
+            k = int(rng.integers(0, I.size))
+            assert D[int(I[k]), int(J[k])].new().value == X[k]      # element lookup straight after the product
+            D = A.mxm(A, sr).new()
+            ok, msg = H.mat_equal(D.T.new(), R.BigMat.from_coo(J, I, X, n, n))
+            assert ok, msg
+            D = A.mxm(A, sr).new()
+            D.wait("materialize")
+            ok, msg = H.mat_equal(D, C2b)
+            assert ok, msg
+            D = A.mxm(A, sr).new()
+            x = H.random_values(rng, n, dtype)
+            w = D.mxv(gb.Vector.from_coo(np.arange(n), x, size=n), sr).new()
+            ok, msg = H.vec_equal(w, R.mxv_T(semiring, C2b, R.BigVec(x, np.ones(n, np.uint8))))
+            assert ok, msg
+            D = A.mxm(A, sr).new()
+            E = D.ewise_add(A, gb.binary.plus if dtype != np.bool_ else gb.binary.lor).new()
+            assert E.nvals >= D.nvals
+            # accumulate a row-end product into an existing matrix (write-back merges need the compact, sorted form)
+            Cg = gb.Matrix.from_coo(r, c, v, nrows=n, ncols=n)
+            Cg(gb.binary.plus) << A.mxm(A, sr)
+            want = R.mxm(Ab, None, "plus", semiring, Ab, Ab)
+            ok, msg = H.mat_equal(Cg, want)
+            assert ok, msg
+        finally:
+            gb.cuda.set_option("spgemm_row_end", None)
+
+
 @pytest.mark.parametrize("opts", [{}, {"spgemm_tile_ctas": "1", "spgemm_tile_threads": "512"}, {"spgemm_tile_scap": "512", "spgemm_tile_tcap": "2048"}])
 @pytest.mark.parametrize("dtype,semiring", [(np.float32, "plus_times"), (np.int64, "min_plus"), (np.float64, "plus_second"), (np.int32, "any_pair")])
 def test_mxm_tiled_kernel_vs_oracle(gb, dtype, semiring, opts):
