@@ -34,10 +34,13 @@ for t in TYPES:
 emit("GrB_UnaryOp", "GrB_LNOT", '{UOP_LNOT, TC_BOOL, "GrB_LNOT"}')
 for t in INTS:
     emit("GrB_UnaryOp", f"GrB_BNOT_{t}", f'{{UOP_BNOT, TC_{t}, "GrB_BNOT_{t}"}}')
+for t in ["FP32", "FP64"]:   # the floating-point GxB unary ops the aggregator finalizers and PageRank-style recipes use
+    for op in ["SQRT", "EXP", "LOG", "EXP2", "LOG2", "LOG10", "FLOOR", "CEIL", "ROUND", "TRUNC", "SIGNUM"]:
+        emit("GrB_UnaryOp", f"GxB_{op}_{t}", f'{{UOP_{op}, TC_{t}, "GxB_{op}_{t}"}}')
 
 # ---- binary
 GRB_BIN = ["FIRST", "SECOND", "MIN", "MAX", "PLUS", "MINUS", "TIMES", "DIV"]
-GXB_BIN = ["RMINUS", "RDIV", "PAIR", "ANY", "LOR", "LAND", "LXOR", "ISEQ", "ISNE"]
+GXB_BIN = ["RMINUS", "RDIV", "PAIR", "ANY", "LOR", "LAND", "LXOR", "ISEQ", "ISNE", "POW"]
 CMP = ["EQ", "NE", "GT", "LT", "GE", "LE"]
 for t in TYPES:
     for op in GRB_BIN:
@@ -64,7 +67,7 @@ emit("GrB_Monoid", "GxB_EQ_BOOL_MONOID", '{OP_LXNOR, TC_BOOL, "GxB_EQ_BOOL_MONOI
 GRB_SR = {("PLUS", "TIMES"), ("PLUS", "MIN"), ("MIN", "PLUS"), ("MIN", "TIMES"), ("MIN", "FIRST"), ("MIN", "SECOND"),
           ("MIN", "MAX"), ("MAX", "PLUS"), ("MAX", "TIMES"), ("MAX", "FIRST"), ("MAX", "SECOND"), ("MAX", "MIN")}
 ADDS = ["PLUS", "TIMES", "MIN", "MAX", "ANY"]
-MULS = ["FIRST", "SECOND", "PAIR", "MIN", "MAX", "PLUS", "MINUS", "RMINUS", "TIMES", "DIV", "RDIV", "LOR", "LAND", "LXOR"]
+MULS = ["FIRST", "SECOND", "PAIR", "MIN", "MAX", "PLUS", "MINUS", "RMINUS", "TIMES", "DIV", "RDIV", "LOR", "LAND", "LXOR", "ISEQ", "ISNE", "POW"]
 for t in NUM:
     for a in ADDS:
         for m in MULS:

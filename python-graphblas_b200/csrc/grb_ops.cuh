@@ -45,6 +45,7 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return gbool(x.v < y.v);
             case OP_GE: return gbool(x.v >= y.v);
             case OP_LE: return gbool(x.v <= y.v);
+            case OP_POW: return gbool(x.v || !y.v);
         }
         return x;
     } else if constexpr (std::is_floating_point<T>::value) {
@@ -70,6 +71,7 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
+            case OP_POW: return (T)pow(x, y);
         }
         return x;
     } else {
@@ -102,6 +104,15 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
+            case OP_POW: {   // through double, saturating, NaN -> 0 (how SuiteSparse defines integer pow)
+                const double r = pow((double)x, (double)y);
+                if (r != r) return (T)0;
+                const T tmin = std::is_signed<T>::value ? (T)((U)1 << (sizeof(T) * 8 - 1)) : (T)0;
+                const T tmax = std::is_signed<T>::value ? (T)(~((U)1 << (sizeof(T) * 8 - 1))) : (T)~(U)0;
+                if (r <= (double)tmin) return tmin;
+                if (r >= (double)tmax) return tmax;
+                return (T)r;
+            }
         }
         return x;
     }

@@ -84,7 +84,9 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
             }
         }
     }
-    // returns 1 when the key was new
+    // returns 1 when the key was new.  GUARD: trap when the table is full instead of probing for ever (split rows size their
+    // tables from an expectation, not from an upper bound)
+    template <bool GUARD = false>
     __device__ __forceinline__ int insert(const SR &sr, int j, T p) {
         unsigned h = hash_slot(j, size);
         if (kPacked) {
@@ -101,7 +103,7 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
                         return 0;
                     }
                     h = (h + 1 == size) ? 0 : h + 1;
-                    if (--budget == 0) __trap();
+                    if (GUARD && --budget == 0) __trap();
                 }
             }
             while (true) {
@@ -130,7 +132,7 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
                     return fresh;
                 }
                 h = (h + 1 == size) ? 0 : h + 1;
-                if (--budget == 0) __trap();
+                if (GUARD && --budget == 0) __trap();
             }
         }
     }
@@ -423,8 +425,11 @@ spgemm_warp_kernel(SR sr, const int32_t *__restrict__ rows, int64_t n_rows, int 
 // how short the B rows are.  GLOBAL selects a global-memory table (rows too big for shared memory); it is a
 // template parameter so that the shared-memory instantiation compiles to ATOMS/LDS/STS rather than generic atomics.
 constexpr int UNROLL = 4;
-template <typename SR, typename T, bool NUMERIC, bool PACK, bool GLOBAL>
-__global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, int flags, const int64_t *__restrict__ cnt,
+#ifndef SPGEMM_PIPE
+#define SPGEMM_PIPE 0   // measured: 37.74 (pipelined) vs 37.75 ms (plain) for the CTA bins of the scale-22 product, and 12 more registers
+#endif
+template <typename SR, typename T, bool NUMERIC, bool PACK, bool GLOBAL, bool SPLIT = false>
+__global__ void __launch_bounds__(MAX_THREADS) spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int cap, int tf8, int flags, const int64_t *__restrict__ cnt,
                                     const int64_t *__restrict__ Ap, const int64_t *__restrict__ Ae, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
                                     const int64_t *__restrict__ Bp, const int64_t *__restrict__ Be, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
                                     int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *__restrict__ Oj,
@@ -449,7 +454,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
     // (the order of a row's entries is free: results are "jumbled" anyway).
     int parts = 1, part = 0;
     int64_t row;
-    if (part_offs) {
+    if (SPLIT) {
         int lo = 0, hi = n_split_rows - 1;
         const int64_t me = blockIdx.x;
         while (lo < hi) {
@@ -474,7 +479,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         tab.bind(kbase, sz, vbase, flags & 1);
     } else {
         // a part expects 1 / parts of the row's keys; parts_of() left 1/8 head-room below part_maxc
-        const int64_t c_eff = parts > 1 ? part_maxc : cnt[row];
+        const int64_t c_eff = SPLIT ? part_maxc : cnt[row];
         tab.bind(s_raw, (unsigned)table_size_for(c_eff, cap, tf8), s_raw + (size_t)cap * 4, flags & 1);
     }
     tab.init(sr, tid, nthreads);
@@ -517,12 +522,20 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
         // lanes read consecutive entries of one B row (coalesced), and the owning A entry is found by ONE binary search per
         // step; the later products of the lane lie 32 further on, a short forward walk over the prefix (s_off[nthreads] = P is
         // the sentinel, entries beyond chunk_n hold P as well).
-        for (int seg = warp * (32 * UNROLL); seg < P; seg += nwarps * (32 * UNROLL)) {
-            int jj[UNROLL];
-            T bb[UNROLL], aa[UNROLL];
+        // SPGEMM_PIPE=1: software pipeline -- the loads of the warp's NEXT step are issued before the inserts of the current one, so
+        // the L2 round trip of Bj / Bx overlaps the shared-memory atomics (the compiler cannot move loads across them).  Measured
+        // neutral (the SM is short of warps, not of loads in flight: 6 CTAs x 4 warps, 13 cycles per issued instruction), so off.
+        // Every warp owns ONE contiguous range of the chunk's products (P / nwarps, rounded up to whole warp rows of 32) and walks it
+        // in steps of 32 * UNROLL: all warps do the same amount of work to within 32 products.  (Handing out 128-product steps
+        // round-robin left a 1 100-product row as 3 + 2 + 2 + 2 steps over four warps: ncu showed 20 % of the samples of the
+        // largest bin waiting at the barrier below, profiles/ncu_full_spgemm_r02.txt.)
+        const int per_warp = (((P + nwarps - 1) / nwarps) + 31) & ~31;
+        const int w_beg = warp * per_warp;
+        const int w_end = w_beg + per_warp < P ? w_beg + per_warp : P;
+        auto load_step = [&](int seg, int (&jj)[UNROLL], T (&bb)[UNROLL], T (&aa)[UNROLL]) {
             int p = seg + wlane;
             int lo = 0;
-            if (p < P) {
+            if (p < w_end) {
                 int hi = chunk_n - 1;   // last entry e with s_off[e] <= p (zero-length rows are skipped)
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
@@ -533,7 +546,7 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 jj[u] = HASH_EMPTY;
-                if (p < P) {
+                if (p < w_end) {
                     while (s_off[lo + 1] <= p) lo++;
                     const int64_t q = s_bs[lo] + (p - s_off[lo]);
                     jj[u] = Bj[q];
@@ -542,20 +555,49 @@ __global__ void spgemm_block_kernel(SR sr, const int32_t *__restrict__ rows, int
                 }
                 p += 32;
             }
+        };
+        auto insert_step = [&](const int (&jj)[UNROLL], const T (&bb)[UNROLL], const T (&aa)[UNROLL]) {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 if (jj[u] == HASH_EMPTY) continue;
-                if (parts > 1 && part_of_key(jj[u], parts) != part) continue;
+                if (SPLIT && part_of_key(jj[u], parts) != part) continue;
                 T pr = T();
                 if (NUMERIC) pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
-                local_new += mk.Mp ? (mk.comp ? tab.insert_comp(sr, jj[u], pr) : tab.accumulate_masked(sr, jj[u], pr)) : tab.insert(sr, jj[u], pr);
+                local_new += mk.Mp ? (mk.comp ? tab.insert_comp(sr, jj[u], pr) : tab.accumulate_masked(sr, jj[u], pr)) : tab.template insert<SPLIT>(sr, jj[u], pr);
+            }
+        };
+        const int step = 32 * UNROLL;
+#if SPGEMM_PIPE
+        {
+            int jj[UNROLL], nj[UNROLL];
+            T bb[UNROLL], aa[UNROLL], nb[UNROLL], na[UNROLL];
+            int seg = w_beg;
+            if (seg < w_end) load_step(seg, jj, bb, aa);
+            while (seg < w_end) {
+                const int nseg = seg + step;
+                const bool more = nseg < w_end;   // warp-uniform
+                if (more) load_step(nseg, nj, nb, na);
+                insert_step(jj, bb, aa);
+                if (more) {
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) { jj[u] = nj[u]; bb[u] = nb[u]; aa[u] = na[u]; }
+                }
+                seg = nseg;
             }
         }
+#else
+        for (int seg = w_beg; seg < w_end; seg += step) {
+            int jj[UNROLL];
+            T bb[UNROLL], aa[UNROLL];
+            load_step(seg, jj, bb, aa);
+            insert_step(jj, bb, aa);
+        }
+#endif
         __syncthreads();   // s_* arrays are rewritten by the next chunk
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_new += __shfl_down_sync(0xffffffffu, local_new, o);
-    if (parts > 1) {
+    if (SPLIT) {
         // this CTA's piece: its size is the number of keys it opened; one atomic on the row's counter places it
         if (wlane == 0 && local_new) atomicAdd(&s_new, local_new);
         __syncthreads();
@@ -798,7 +840,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 if (!sinfo) {
                     const int scap = bins.spec.cap[BIN_LAST_SHARED], sthreads = bins.spec.threads[BIN_LAST_SHARED];
                     const size_t smem = (((size_t)scap * entry + 15) & ~(size_t)15) + block_stage_bytes(sthreads, sizeof(T));
-                    auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
+                    auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false, true>;
                     CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                     LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_split" : "spgemm_symbolic_split");
                     kern<<<(unsigned)bins.split_parts, sthreads, smem, g_stream>>>(sr, rows, scap, bins.spec.tf8[BIN_LAST_SHARED], bins.spec.flags, a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, nullptr, nullptr, a.mk, poffs, (int)n, maxc);

@@ -106,6 +106,17 @@ template <typename T> __device__ __forceinline__ T unop(int op, T x) {
             case UOP_LNOT: return (T)(x == 0);
             case UOP_ABS: return x < 0 ? -x : x;
             case UOP_ONE: return (T)1;
+            case UOP_SQRT: return sqrt(x);     // correctly rounded in both precisions (no fast-math)
+            case UOP_EXP: return exp(x);
+            case UOP_LOG: return log(x);
+            case UOP_EXP2: return exp2(x);
+            case UOP_LOG2: return log2(x);
+            case UOP_LOG10: return log10(x);
+            case UOP_FLOOR: return floor(x);
+            case UOP_CEIL: return ceil(x);
+            case UOP_ROUND: return rint(x);    // GxB_ROUND: C round-half-even is what numpy / the reference's tests expect of rint
+            case UOP_TRUNC: return trunc(x);
+            case UOP_SIGNUM: return x != x ? x : (T)((x > 0) - (x < 0));
             default: return x;
         }
     } else {

@@ -53,5 +53,6 @@ from .scalar import Scalar  # noqa: E402
 from .vector import Vector  # noqa: E402
 from . import cuda  # noqa: E402
 from . import io  # noqa: E402
+from . import agg  # noqa: E402
 
-__all__ = ["Matrix", "Vector", "Scalar", "semiring", "binary", "monoid", "unary", "select", "dtypes", "replace", "init", "cuda", "io"]
+__all__ = ["Matrix", "Vector", "Scalar", "semiring", "binary", "monoid", "unary", "select", "dtypes", "replace", "init", "cuda", "io", "agg"]

@@ -12,7 +12,7 @@ import os
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-_SO = _HERE / "libgrb_cuda.so"
+_SO = pathlib.Path(os.environ.get("GRB_CUDA_LIB") or (_HERE / "libgrb_cuda.so"))   # GRB_CUDA_LIB: an A/B build of the same library
 
 GrB_Index = ctypes.c_uint64
 _info_funcs_void_p = {"GrB_cuda_lookup", "GrB_cuda_get_stream"}

@@ -277,15 +277,21 @@ class Matrix(BaseType):
         """reference core/matrix.py:2600-2650 (GrB_Matrix_reduce_Monoid): w(i) = (+)_j A(i, j) over the entries of row i; rows
         without entries give no entry.  Run as ONE pull SpMV with the semiring <monoid>_first against an all-present vector:
         first(a, x) = a, so the multiply passes A's values through and the vector's values are never read."""
+        if getattr(op, "opclass", None) == "Aggregator":   # a recipe over the multiply (graphblas_b200/agg.py)
+            return op._rowwise_expr(self)
         return _reduce_to_vector(self, op, "reduce_rowwise")
 
     def reduce_columnwise(self, op=None):
         """reference core/matrix.py:2652-2701: the row-wise reduction of the transpose (GrB_DESC_T0)"""
+        if getattr(op, "opclass", None) == "Aggregator":
+            return op._rowwise_expr(self.T)
         return _reduce_to_vector(self.T, op, "reduce_columnwise")
 
     def reduce_scalar(self, op=None, *, allow_empty=True):
         """reference core/matrix.py:2703-2760: GrB_Matrix_reduce_Monoid_Scalar into a GrB_Scalar, or (allow_empty=False)
         GrB_Matrix_reduce_<T> into a C scalar"""
+        if getattr(op, "opclass", None) == "Aggregator":
+            return op._scalar_expr(self, True)
         op = operator.monoid.plus if op is None else op
         op = operator.get_typed_op(op, self.dtype, kind="monoid")
         if op.opclass != "Monoid":
@@ -412,9 +418,13 @@ class TransposedMatrix:
         return _select(self, op, thunk)
 
     def reduce_rowwise(self, op=None):
+        if getattr(op, "opclass", None) == "Aggregator":
+            return op._rowwise_expr(self)
         return _reduce_to_vector(self, op, "reduce_rowwise")
 
     def reduce_columnwise(self, op=None):
+        if getattr(op, "opclass", None) == "Aggregator":
+            return op._rowwise_expr(self._matrix)
         return _reduce_to_vector(self._matrix, op, "reduce_columnwise")
 
     def new(self, dtype=None, *, name=None):

@@ -158,9 +158,9 @@ def initialize():
     re_mon_grb = re.compile(rf"^GrB_(PLUS|TIMES|MIN|MAX|LOR|LAND|LXOR|LXNOR)_MONOID_({_TYPES})$")
     re_mon_gxb = re.compile(rf"^GxB_(ANY|EQ)_({_TYPES})_MONOID$")
     re_bin = re.compile(rf"^G[rx]B_(FIRST|SECOND|ONEB|PAIR|MIN|MAX|PLUS|MINUS|RMINUS|TIMES|DIV|RDIV|ANY|LOR|LAND|LXOR|"
-                        rf"ISEQ|ISNE|EQ|NE|GT|LT|GE|LE)_({_TYPES})$")
+                        rf"ISEQ|ISNE|POW|EQ|NE|GT|LT|GE|LE)_({_TYPES})$")
     re_bin_bool = re.compile(r"^GrB_(LOR|LAND|LXOR|LXNOR)$")
-    re_un = re.compile(rf"^G[rx]B_(IDENTITY|AINV|MINV|ABS|ONE|LNOT|BNOT)_({_TYPES})$")
+    re_un = re.compile(rf"^G[rx]B_(IDENTITY|AINV|MINV|ABS|ONE|LNOT|BNOT|SQRT|EXP|LOG|EXP2|LOG2|LOG10|FLOOR|CEIL|ROUND|TRUNC|SIGNUM)_({_TYPES})$")
     re_sel_pos = re.compile(r"^GrB_(TRIL|TRIU|DIAG|OFFDIAG|COLLE|COLGT|ROWLE|ROWGT)$")
     re_sel_val = re.compile(rf"^GrB_(VALUEEQ|VALUENE|VALUEGT|VALUEGE|VALUELT|VALUELE)_({_TYPES})$")
     semiring_names = set()

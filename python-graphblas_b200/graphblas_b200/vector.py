@@ -331,6 +331,8 @@ class Vector(BaseType):
     def reduce(self, op=None, *, allow_empty=True):
         """reference core/vector.py:1633-1690: GrB_Vector_reduce_Monoid_Scalar into a GrB_Scalar (an empty vector gives an empty
         scalar); allow_empty=False reduces into a C scalar with GrB_Vector_reduce_<T> (an empty vector gives the identity)."""
+        if getattr(op, "opclass", None) == "Aggregator":   # a recipe over the multiply (graphblas_b200/agg.py)
+            return op._scalar_expr(self, False)
         op = operator.monoid.plus if op is None else op
         op = operator.get_typed_op(op, self.dtype, kind="monoid")
         if op.opclass != "Monoid":
