@@ -319,6 +319,7 @@ GrB_Info GrB_cuda_Vector_import_dense(GrB_Vector *v, GrB_Type type, GrB_Index n,
                                       const uint8_t *present /* NULL = full */, int on_device);
 GrB_Info GrB_cuda_Vector_export_dense(void *vals, uint8_t *present, const GrB_Vector v);
 GrB_Info GrB_cuda_Vector_touch(GrB_Vector v); /* arrays were modified through device_arrays(): drop caches */
+GrB_Info GrB_cuda_Vector_assume_full(GrB_Vector v); /* ... and the caller vouches that every position now holds an entry (no recount) */
 GrB_Info GrB_cuda_Matrix_sort(GrB_Matrix A);          /* finish a lazily "jumbled" result now */
 /* squeeze a row-end product (rows in order, unused slots between them: how GrB_mxm leaves a result that hardly compresses)
    into the compact CSR now; a no-op on a compact matrix.  GrB_Matrix_wait(A, GrB_MATERIALIZE) does this and the sort. */

@@ -17,7 +17,7 @@ enum TypeCode : int {
 enum OpCode : int {
     OP_NONE = 0, OP_FIRST = 1, OP_SECOND, OP_PAIR, OP_PLUS, OP_MINUS, OP_TIMES, OP_DIV, OP_MIN, OP_MAX, OP_LOR,
     OP_LAND, OP_LXOR, OP_ANY, OP_RMINUS, OP_RDIV, OP_LXNOR, OP_EQ, OP_NE, OP_GT, OP_LT, OP_GE, OP_LE, OP_ISEQ,
-    OP_ISNE, OP_POW, OP_COUNT
+    OP_ISNE, OP_POW, OP_RPOW /* pow(y, x): internal, the operand swap of vxm */, OP_COUNT
 };
 enum UnaryCode : int { UOP_IDENTITY = 1, UOP_AINV, UOP_MINV, UOP_LNOT, UOP_ABS, UOP_ONE, UOP_BNOT,
                        UOP_SQRT, UOP_EXP, UOP_LOG, UOP_EXP2, UOP_LOG2, UOP_LOG10, UOP_FLOOR, UOP_CEIL, UOP_ROUND, UOP_TRUNC, UOP_SIGNUM };   // floating point only

@@ -46,6 +46,7 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_GE: return gbool(x.v >= y.v);
             case OP_LE: return gbool(x.v <= y.v);
             case OP_POW: return gbool(x.v || !y.v);
+            case OP_RPOW: return gbool(y.v || !x.v);
         }
         return x;
     } else if constexpr (std::is_floating_point<T>::value) {
@@ -72,6 +73,7 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
             case OP_POW: return (T)pow(x, y);
+            case OP_RPOW: return (T)pow(y, x);
         }
         return x;
     } else {
@@ -104,8 +106,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
-            case OP_POW: {   // through double, saturating, NaN -> 0 (how SuiteSparse defines integer pow)
-                const double r = pow((double)x, (double)y);
+            case OP_POW: case OP_RPOW: {   // through double, saturating, NaN -> 0 (how SuiteSparse defines integer pow)
+                const double r = op == OP_POW ? pow((double)x, (double)y) : pow((double)y, (double)x);
                 if (r != r) return (T)0;
                 const T tmin = std::is_signed<T>::value ? (T)((U)1 << (sizeof(T) * 8 - 1)) : (T)0;
                 const T tmax = std::is_signed<T>::value ? (T)(~((U)1 << (sizeof(T) * 8 - 1))) : (T)~(U)0;

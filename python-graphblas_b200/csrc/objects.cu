@@ -389,6 +389,11 @@ extern "C" GrB_Info GrB_cuda_Vector_touch(GrB_Vector v) {
     v->nvals = -1;
     return GrB_SUCCESS;
 }
+extern "C" GrB_Info GrB_cuda_Vector_assume_full(GrB_Vector v) {
+    if (!valid(v)) return GrB_UNINITIALIZED_OBJECT;
+    v->nvals = v->n;
+    return GrB_SUCCESS;
+}
 extern "C" GrB_Info GrB_cuda_Vector_device_arrays(const GrB_Vector v, void **vals, uint8_t **present) {
     if (!valid(v)) return GrB_UNINITIALIZED_OBJECT;
     GRB_TRY(vector_ensure_arrays(v));

@@ -600,7 +600,10 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
     GrB_Matrix A = a.A;
     GrB_Vector u = a.u;
     GrB_Info info = GrB_SUCCESS;
-    GRB_TRY(vector_count(u));
+    // the entry count of u picks the direction of a transposed multiply; a plain pull only uses it to skip the presence bytes of
+    // a full vector, so an unknown count (arrays just refilled by a collective / by peers) is NOT recounted there: that would be
+    // an O(n) kernel plus a host round trip in every iteration of a partitioned loop
+    if (a.use_transpose) GRB_TRY(vector_count(u));
     // decide the traversal: rows of M are directly available (pull) unless M = A' and no CSC twin is wanted
     bool push = false;
     if (a.use_transpose) {
@@ -627,6 +630,8 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             case OP_RMINUS: mul = OP_MINUS; break;
             case OP_DIV: mul = OP_RDIV; break;
             case OP_RDIV: mul = OP_DIV; break;
+            case OP_POW: mul = OP_RPOW; break;
+            case OP_RPOW: mul = OP_POW; break;
             default: break;   // commutative multiplies
         }
     }

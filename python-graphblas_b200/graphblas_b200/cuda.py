@@ -284,6 +284,11 @@ def vector_touch(v):
     call("GrB_cuda_Vector_touch", [v])
 
 
+def vector_assume_full(v):
+    """the arrays were refilled from outside and every position holds an entry: spares the recount (a kernel + a host round trip)"""
+    call("GrB_cuda_Vector_assume_full", [v])
+
+
 def matrix_sort(A):
     call("GrB_cuda_Matrix_sort", [A])
 

@@ -130,7 +130,9 @@ class GatheredVector:
         all_gather_uneven(self._vviews, lv, group)
         if self.sparse:
             all_gather_uneven(self._pviews, lp, group)
-        self.gb.cuda.vector_touch(self.vector)
+            self.gb.cuda.vector_touch(self.vector)
+        else:
+            self.gb.cuda.vector_assume_full(self.vector)
         return self.vector
 
 
@@ -141,11 +143,12 @@ class PeerExchange:
     The only cross-rank operation per iteration is a tiny all-reduce (which SSSP needs anyway for its convergence flag): after
     it, every writer's kernel has completed, so set (k + 1) & 1 is complete everywhere and set k & 1 may be overwritten."""
 
-    def __init__(self, gb, dtype, n, bounds, rank, group=None):
+    def __init__(self, gb, dtype, n, bounds, rank, group=None, *, dense=False):
         import torch
         import torch.distributed as dist
 
         self.gb, self.n, self.bounds, self.rank = gb, n, bounds, rank
+        self.dense = dense   # every position always holds an entry (PageRank, dense mxv): no presence traffic, no recounts
         self.dtype = gb.dtypes.lookup_dtype(dtype)
         world = len(bounds) - 1
         es = self.dtype.np_type.itemsize
@@ -182,7 +185,7 @@ class PeerExchange:
     def writing(self, scale_ptr=None, *, with_presence=True):
         """context manager: multiplies inside it also store their result slice into the NEXT buffer set of every rank"""
         vs, ps = self.targets[(self.step + 1) & 1]
-        return self.gb.cuda.peer_targets(vs, ps if with_presence else None, self.bounds[self.rank], scale_ptr)
+        return self.gb.cuda.peer_targets(vs, ps if (with_presence and not self.dense) else None, self.bounds[self.rank], scale_ptr)
 
     def fill_current(self, local, group=None):
         """first fill of the current set from the ranks' slices (one NCCL all-gather, before the loop)"""
@@ -197,7 +200,10 @@ class PeerExchange:
         world = len(self.bounds) - 1
         all_gather_uneven([vals[self.bounds[g]:self.bounds[g + 1]] for g in range(world)], lv.view(vals.dtype), group)
         all_gather_uneven([pres[self.bounds[g]:self.bounds[g + 1]] for g in range(world)], lp, group)
-        self.gb.cuda.vector_touch(self.current)
+        self._refilled()
+
+    def _refilled(self):
+        (self.gb.cuda.vector_assume_full if self.dense else self.gb.cuda.vector_touch)(self.current)
 
     def advance(self, flag=0.0):
         """cross-rank ordering point of the iteration (max all-reduce of `flag`, returned); then the next set becomes current"""
@@ -207,7 +213,7 @@ class PeerExchange:
         if dist.is_initialized() and dist.get_world_size(self._group) > 1:
             dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self._group)
         self.step += 1
-        self.gb.cuda.vector_touch(self.current)
+        self._refilled()
         return self._flag
 
     def close(self):
@@ -245,10 +251,11 @@ def local_block(gb, indptr, cols, vals, ncols, r0, r1):
                                           r1 - r0, ncols)
 
 
-def sssp_partitioned(gb, Wt_block, bounds, rank, n, src, *, max_iters=64, group=None, exchange="nccl"):
+def sssp_partitioned(gb, Wt_block, bounds, rank, n, src, *, max_iters=64, group=None, exchange="nccl", px=None):
     """Bellman-Ford sweeps d(min) << d.vxm(W, min_plus) on a row partition of W' (BASELINE config 4): rank g owns rows
     bounds[g]..bounds[g + 1] of W' (= columns of W) and the matching slice of d; the full d is all-gathered every sweep.
-    Returns (local slice of d, full gathered d, sweeps).  Bit-identical to the single-GPU loop: min over int64 is exact."""
+    Returns (local slice of d, full gathered d, sweeps).  Bit-identical to the single-GPU loop: min over int64 is exact.
+    `px`: a PeerExchange built beforehand (mapping the peers' buffers is a one-off set-up, not part of an iteration)."""
     import torch
     import torch.distributed as dist
 
@@ -259,7 +266,9 @@ def sssp_partitioned(gb, Wt_block, bounds, rank, n, src, *, max_iters=64, group=
     if exchange == "peer":
         # fused: the epilogue of each sweep's multiply stores the new distances into every rank's next input vector; the
         # all-reduce of the convergence flag is the only collective (and the ordering point) of a sweep
-        px = PeerExchange(gb, gb.dtypes.INT64, n, bounds, rank, group)
+        own_px = px is None
+        if own_px:
+            px = PeerExchange(gb, gb.dtypes.INT64, n, bounds, rank, group)
         try:
             px.fill_current(d_loc, group)
             sweeps = 0
@@ -274,7 +283,8 @@ def sssp_partitioned(gb, Wt_block, bounds, rank, n, src, *, max_iters=64, group=
             full = GatheredVector(gb, gb.dtypes.INT64, n, bounds, sparse=True)
             full.gather(d_loc, group)
         finally:
-            px.close()
+            if own_px:
+                px.close()
         return d_loc, full, sweeps
     full = GatheredVector(gb, gb.dtypes.INT64, n, bounds, sparse=True)
     full.gather(d_loc, group)
@@ -294,7 +304,7 @@ def sssp_partitioned(gb, Wt_block, bounds, rank, n, src, *, max_iters=64, group=
     return d_loc, full, sweeps
 
 
-def pagerank_partitioned(gb, At_block, outdeg_loc, bounds, rank, n, *, iters=20, damping=0.85, group=None, exchange="nccl"):
+def pagerank_partitioned(gb, At_block, outdeg_loc, bounds, rank, n, *, iters=20, damping=0.85, group=None, exchange="nccl", px=None):
     """The notebook recurrence (reference notebooks/Pagerank Demo.ipynb cell 9) on a row partition of A' (BASELINE config 5):
     w = damping * t / d ; r = teleport ; r(plus) << A'.mxv(w, plus_second) ; t = r -- here t, d, r are local slices, w is
     all-gathered (fp64) once per iteration.  Returns the local slice of t."""
@@ -310,7 +320,9 @@ def pagerank_partitioned(gb, At_block, outdeg_loc, bounds, rank, n, *, iters=20,
         # multiply's epilogue (scale = damping / d per local row); per iteration: one assign, one multiply, one tiny all-reduce
         dv, _ = gb.cuda.vector_as_torch(outdeg_loc, sync=False)
         scale = (damping / dv).contiguous()
-        px = PeerExchange(gb, gb.dtypes.FP64, n, bounds, rank, group)
+        own_px = px is None
+        if own_px:
+            px = PeerExchange(gb, gb.dtypes.FP64, n, bounds, rank, group, dense=True)
         try:
             w0 = gb.cuda.vector_from_torch((scale / n).contiguous())   # w of the first iteration: damping * (1 / n) / d
             px.fill_current(w0, group)
@@ -323,7 +335,8 @@ def pagerank_partitioned(gb, At_block, outdeg_loc, bounds, rank, n, *, iters=20,
                 t = r
             gb.cuda.sync()
         finally:
-            px.close()
+            if own_px:
+                px.close()
         return t
     full = GatheredVector(gb, gb.dtypes.FP64, n, bounds, sparse=False)
     for _ in range(iters):
