@@ -535,7 +535,9 @@ def run_ours(args):
         deg = (indptr[1:] - indptr[:-1])
         rowflops = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         rowflops[1:].index_add_(0, torch.repeat_interleave(torch.arange(n, device=dev), deg), deg[cols.long()])
-        b = D.row_blocks_by_prefix(torch.cumsum(rowflops, 0).cpu().numpy(), world)
+        cost = torch.zeros(n + 1, dtype=torch.float64, device=dev)
+        cost[1:] = D.mxm_row_costs(rowflops[1:])
+        b = D.row_blocks_by_prefix(torch.cumsum(cost, 0).cpu().numpy(), world)
         return b[rank], b[rank + 1]
 
     # ---------------- inputs: every rank generates the matrix from the seed itself (B = A replicated, no input traffic)
@@ -833,7 +835,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(scale=scale)},
-        "problem": {"n": n, "nnz_A": nnz, "nnz_C": int(nnz_c), "flops": int(flops), "parallelism": f"row-partition x{world} (equal flops), B replicated",
+        "problem": {"n": n, "nnz_A": nnz, "nnz_C": int(nnz_c), "flops": int(flops), "parallelism": f"row-partition x{world} (equal estimated cost: flops, split rows weighted), B replicated",
                     "l2": "inputs (0.5 GB) and outputs (>=GBs) exceed the 126 MB L2",
                     "result_form": "row-end CSR (rows in order, unused slots between rows where products merged), columns unsorted inside a row; "
                                    "compaction and sort happen on demand and are reported in phases_ms"},
@@ -874,10 +876,13 @@ def run_scale25(gb, torch, dist, D, dev, rank, world, barrier, max_over_ranks, s
     rowflops = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     rowflops[1:].index_add_(0, torch.repeat_interleave(torch.arange(n, device=dev), deg), deg[cols.long()])
     cum = torch.cumsum(rowflops, 0)
+    cost = torch.zeros(n + 1, dtype=torch.float64, device=dev)
+    cost[1:] = D.mxm_row_costs(rowflops[1:])
     del rowflops
     cum_h = cum.cpu().numpy()
     total_flops = int(cum_h[-1])
-    b = D.row_blocks_by_prefix(cum_h, world)
+    b = D.row_blocks_by_prefix(torch.cumsum(cost, 0).cpu().numpy(), world)   # ranks: equal estimated cost (heavy rows weigh more)
+    del cost
     r0, r1 = b[rank], b[rank + 1]
     # blocks of at most ~3e9 products: result (8 B / entry) + staging stay below ~50 GB
     my_flops = int(cum_h[r1] - cum_h[r0])

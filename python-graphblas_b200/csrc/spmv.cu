@@ -210,7 +210,25 @@ spmv_merge_kernel(SR sr, int64_t nrows, int64_t nnz, const int64_t *__restrict__
                 t_vals[row] = h ? v : T();
                 t_present[row] = (uint8_t)h;
             } else {
-                epi_write(epi, row, v, h, t_vals, t_present);
+                epi_write<T, false>(epi, row, v, h, t_vals, t_present);
+            }
+        }
+    }
+    // Fused exchange: the rows that ended in this tile form ONE contiguous run of the output; the CTA pushes that run
+    // into the next input vector of every rank with coalesced stores (consecutive lanes -> consecutive positions: whole 128-byte
+    // NVLink packets) instead of one scattered store per row and peer from the emission loop above -- measured 6.1 -> see
+    // DESIGN.md section 5.  A row that began in an earlier tile is finished (and pushed) by the fix-up kernel.
+    if (epi.active && epi.npeer) {
+        __syncthreads();   // this CTA's own global writes above are visible to all of its threads
+        for (int i = (carry_in ? 1 : 0) + tid; i < tile_rows; i += SPMV_BLOCK) {
+            const int64_t row = r0 + i;
+            const uint8_t p = t_present[row];
+            T out = p ? t_vals[row] : T();
+            if (p && epi.pscale) out = binop<T>(OP_TIMES, out, epi.pscale[row]);
+#pragma unroll 1
+            for (int k = 0; k < epi.npeer; k++) {
+                epi.pv[k][epi.poff + row] = out;
+                if (epi.pp[k]) epi.pp[k][epi.poff + row] = p;
             }
         }
     }
@@ -449,7 +467,10 @@ static GrB_Info run_pull(const SR &sr, CsrArrays &M, int64_t mrows, int64_t nnz,
     int trial_cls = -1;
     static cudaEvent_t trial_ev[2] = {nullptr, nullptr};
     // the banded kernel reads the matrix values in place (no typecast copy) and produces plain T
-    const bool band_ok = native_val_type >= 0 && !epi.active && !flip && opt_get_int("spmv_band", 1) != 0;
+    // (opt-in for the timed trial -- option spmv_band=1 -- or forced with spmv=band: building its second, band-major copy of the
+    // matrix costs a sort of all entries, and on the bench matrices it only wins for sparse input vectors: 449 vs 498 us)
+    const bool band_forced = !strcmp(method, "band");
+    const bool band_ok = native_val_type >= 0 && !epi.active && !flip && (band_forced || opt_get_int("spmv_band", 0) != 0);
     const int n_cand = band_ok && nnz >= opt_get_int("spmv_band_min_nnz", 1 << 22) ? 4 : 3;
     if (!strcmp(method, "seg")) candidate = 2;
     else if (!strcmp(method, "band")) candidate = band_ok ? 4 : 1;
@@ -654,7 +675,7 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
                 // fused) plus the separate O(n) write-back pass beats the fused merge-path kernel (SSSP: 455 vs 580 us)
                 // ... and for every width when the banded kernel (plain output only) has won this CSR's timed trial or is asked for
                 const int cls = sizeof(T) >= 8 ? 1 : 0;
-                const bool band_wins = M.pull_choice[cls] == 4 || M.pull_choice[cls] == 0 || !strcmp(opt_get("spmv", "auto"), "band");
+                const bool band_wins = !strcmp(opt_get("spmv", "auto"), "band") || (opt_get_int("spmv_band", 0) != 0 && (M.pull_choice[cls] == 4 || M.pull_choice[cls] == 0));
                 const bool unfuse = a.epi && !a.epi->peer && !a.mask && !a.epi->has_mask && (sizeof(T) >= 8 || band_wins) &&
                                     (!strcmp(opt_get("spmv", "auto"), "auto") || !strcmp(opt_get("spmv", "auto"), "band")) &&
                                     A->nvals >= opt_get_int("spmv_trial_min_nnz", 1 << 20) && opt_get_int("spmv_unfuse_wide", 1) != 0;

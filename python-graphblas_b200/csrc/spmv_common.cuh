@@ -63,7 +63,8 @@ template <typename T> struct VecEpi {
     T *pv[MAX_PEERS];
     uint8_t *pp[MAX_PEERS];
 };
-template <typename T>
+// PEER = false: the caller pushes whole runs of finished rows to the peers itself (merge-path kernel: one coalesced run per tile)
+template <typename T, bool PEER = true>
 __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, int tp, T *__restrict__ w_vals,
                                           uint8_t *__restrict__ w_present) {
     if (!e.active) {
@@ -86,7 +87,7 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
     }
     w_vals[row] = zp ? z : T();
     w_present[row] = zp ? 1 : 0;
-    if (e.npeer) {
+    if (PEER && e.npeer) {
         const T out = zp ? (e.pscale ? binop<T>(OP_TIMES, z, e.pscale[row]) : z) : T();
 #pragma unroll 1
         for (int k = 0; k < e.npeer; k++) {

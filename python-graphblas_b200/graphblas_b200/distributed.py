@@ -29,6 +29,19 @@ def row_blocks_by_prefix(prefix, world):
     return [int(b) for b in np.maximum.accumulate(bounds)]
 
 
+def mxm_row_costs(rowflops, *, split_above=10440, reread=0.25):
+    """Per-row cost estimate of the hash SpGEMM for the row partition of A: the flop bound, except that a row too big for one
+    shared-memory table is hashed by ceil(1.125 flops / split_above) CTAs which ALL stream the row's products (csrc/spgemm.cu,
+    split rows) -- its cost grows by `reread` per extra part.  Balancing this instead of the plain flops keeps the rank that
+    owns the heavy low-index rows of an R-MAT matrix from finishing last (8 GPUs, scale 22: 6.46 -> see DESIGN.md section 5).
+    `rowflops`: torch tensor or numpy array; returns the same kind (float64)."""
+    f = rowflops.double() if hasattr(rowflops, "double") else np.asarray(rowflops, dtype=np.float64)
+    parts = (f * 1.125 / split_above).ceil() if hasattr(f, "ceil") else np.ceil(f * 1.125 / split_above)
+    extra = (parts - 1).clamp(min=0) if hasattr(parts, "clamp") else np.maximum(parts - 1, 0)
+    extra = extra * (f > split_above)   # rows that fit one table are not split at all
+    return f * (1.0 + reread * extra)
+
+
 def slice_csr(indptr, cols, vals, r0, r1):
     """Rows [r0, r1) of a CSR given as array-likes supporting slicing (numpy arrays or torch tensors)."""
     k0, k1 = int(indptr[r0]), int(indptr[r1])
