@@ -17,3 +17,5 @@ try:
 except Exception as e:
     print('parse failed', e)
 PY
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-400
