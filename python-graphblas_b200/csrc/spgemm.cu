@@ -136,6 +136,37 @@ template <typename SR, typename T, bool NUMERIC, bool PACK> struct HashTable {
             }
         }
     }
+    // insert that also reports WHERE the key lives (for the slot list of spgemm_rows_kernel); returns 1 when the key was new
+    __device__ __forceinline__ int insert_at(const SR &sr, int j, T p, unsigned &slot) {
+        unsigned h = hash_slot(j, size);
+        if (kPacked) {
+            const unsigned long long mine = pack_entry<T>(j, p);
+            while (true) {
+                const unsigned long long cur = atomicCAS(&ent[h], HASH_EMPTY64, mine);
+                if (cur == HASH_EMPTY64) { slot = h; return 1; }
+                if ((int)(cur >> 32) == j) {
+                    atomic_combine(sr, reinterpret_cast<T *>(&ent[h]), p);
+                    return 0;
+                }
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        } else {
+            while (true) {
+                int cur = keys[h];
+                int fresh = 0;
+                if (cur == HASH_EMPTY) {
+                    cur = atomicCAS(&keys[h], HASH_EMPTY, j);
+                    if (cur == HASH_EMPTY) { fresh = 1; cur = j; }
+                }
+                if (cur == j) {
+                    if (NUMERIC) atomic_combine(sr, &vals[h], p);
+                    slot = h;
+                    return fresh;
+                }
+                h = (h + 1 == size) ? 0 : h + 1;
+            }
+        }
+    }
     // ---- masked product (C<M> = A*B, M not complemented): the row's table is pre-loaded with the mask row's columns,
     // each tagged MASK_FLAG ("allowed, nothing accumulated yet").  A product whose column is not in the table is dropped
     // before any arithmetic is stored; the first product that hits a column clears the tag (idempotent atomicAnd),
@@ -623,6 +654,153 @@ __global__ void __launch_bounds__(MAX_THREADS) spgemm_block_kernel(SR sr, const 
     }
 }
 
+// ------------------------------------------------------------------ persistent CTA-per-row kernel with a slot list (unmasked numeric)
+// The CTA-per-row kernel above pays for its table twice per row: it clears all 2.5 x count slots before and scans all of them
+// after the inserts (ncu, 4096-slot bin: 43.7 M warp-iterations each for 18.6 M insert steps; the scan with its warp-aggregated
+// compaction is 15 % of the kernel).  Here a CTA stays resident and walks rows rows[b], rows[b + G], ...; every product that
+// OPENS a slot appends the slot's index to a list -- kept in the row's own, still unused output slots Oj[Op[row] ...] (one
+// coalesced 128-byte store per warp step, L2 resident) -- so the drain touches exactly the used slots: entry -> final (column,
+// value) at the list position, fully coalesced, and the slot is reset to EMPTY on the way, which leaves the table clean for the
+// CTA's next row: no clear pass, no scan, no per-slot compaction atomics.
+template <typename SR, typename T, bool PACK>
+__global__ void __launch_bounds__(MAX_THREADS)
+spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap, int tf8, const int64_t *__restrict__ cnt,
+                   const int64_t *__restrict__ Ap, const int64_t *__restrict__ Ae, const int32_t *__restrict__ Aj, const T *__restrict__ Ax,
+                   const int64_t *__restrict__ Bp, const int64_t *__restrict__ Be, const int32_t *__restrict__ Bj, const T *__restrict__ Bx,
+                   int64_t *__restrict__ row_nnz, const int64_t *__restrict__ Op, int32_t *Oj, T *Ox) {
+    typedef HashTable<SR, T, true, PACK> Table;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_wsum[MAX_THREADS / 32];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const size_t tbytes = (((size_t)cap * Table::entry_bytes() + 15) & ~(size_t)15);
+    int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + tbytes);
+    int *s_off = reinterpret_cast<int *>(s_bs + nthreads);
+    T *s_av = reinterpret_cast<T *>(s_off + ((nthreads + 4) & ~3));
+    const int wlane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const unsigned lt_mask = (1u << wlane) - 1u;
+
+    Table tab;
+    tab.bind(s_raw, (unsigned)cap, s_raw + (size_t)cap * 4, 1);
+    tab.init(sr, tid, nthreads);   // the only full clear: every row's drain leaves the table empty again
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int64_t row = rows[r];
+        tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4, 1);
+        const int64_t ob = Op[row];
+        int32_t *lj = Oj + ob;
+        const int64_t a_beg = Ap[row], a_end = Ae[row];
+        for (int64_t c0 = a_beg; c0 < a_end; c0 += nthreads) {
+            const int chunk_n = (int)((a_end - c0 < nthreads) ? (a_end - c0) : nthreads);
+            int len = 0;
+            if (tid < chunk_n) {
+                const int64_t k = c0 + tid;
+                const int32_t br = Aj[k];
+                const int64_t bs = Bp[br];
+                len = (int)(Be[br] - bs);
+                s_bs[tid] = bs;
+                if (sr.reads_a()) s_av[tid] = Ax[k];
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (wlane >= o) incl += up;
+            }
+            if (wlane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < warp; w++) base += s_wsum[w];
+            s_off[tid] = base + incl - len;
+            if (tid == nthreads - 1) s_off[nthreads] = base + incl;
+            __syncthreads();
+            const int P = s_off[nthreads];
+            const int per_warp = (((P + nwarps - 1) / nwarps) + 31) & ~31;   // one contiguous range of the chunk's products per warp
+            const int w_beg = warp * per_warp;
+            const int w_end = w_beg + per_warp < P ? w_beg + per_warp : P;
+            for (int seg = w_beg; seg < w_end; seg += 32 * UNROLL) {
+                int jj[UNROLL];
+                T bb[UNROLL], aa[UNROLL];
+                int p = seg + wlane;
+                int lo = 0;
+                if (p < w_end) {
+                    int hi = chunk_n - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_off[mid] <= p) lo = mid;
+                        else hi = mid - 1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    jj[u] = HASH_EMPTY;
+                    if (p < w_end) {
+                        while (s_off[lo + 1] <= p) lo++;
+                        const int64_t q = s_bs[lo] + (p - s_off[lo]);
+                        jj[u] = Bj[q];
+                        if (sr.reads_b()) bb[u] = Bx[q];
+                        if (sr.reads_a()) aa[u] = s_av[lo];
+                    }
+                    p += 32;
+                }
+                unsigned slot[UNROLL], fm[UNROLL];
+                int fresh[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    fresh[u] = 0;
+                    slot[u] = 0;
+                    if (jj[u] != HASH_EMPTY) {
+                        const T pr = sr.mul(sr.reads_a() ? aa[u] : one_of<T>(), sr.reads_b() ? bb[u] : one_of<T>());
+                        fresh[u] = tab.insert_at(sr, jj[u], pr, slot[u]);
+                    }
+                }
+                __syncwarp();
+                // one reservation of list positions per warp step; new slots of the step go out as (at most UNROLL) coalesced runs
+                int total = 0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    fm[u] = __ballot_sync(0xffffffffu, fresh[u] != 0);
+                    total += __popc(fm[u]);
+                }
+                if (total) {
+                    int pos = 0;
+                    if (wlane == 0) pos = atomicAdd(&s_count, total);
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        if (fresh[u]) lj[pos + __popc(fm[u] & lt_mask)] = (int32_t)slot[u];
+                        pos += __popc(fm[u]);
+                    }
+                }
+            }
+            __syncthreads();   // s_* arrays are rewritten by the next chunk; after the last chunk: every insert and list store is done
+        }
+        const int count = s_count;
+        // drain by the list: position i of the row's output receives the entry of slot list[i]; the slot is emptied
+        T *lx = Ox + ob;
+        for (int i = tid; i < count; i += nthreads) {
+            const unsigned sl = (unsigned)lj[i];
+            if (Table::kPacked) {
+                const unsigned long long e = tab.ent[sl];
+                tab.ent[sl] = HASH_EMPTY64;
+                lj[i] = (int)(e >> 32);
+                lx[i] = unpack_value<T>(e);
+            } else {
+                lj[i] = tab.keys[sl];
+                lx[i] = tab.vals[sl];
+                tab.keys[sl] = HASH_EMPTY;
+                tab.vals[sl] = sr.identity();
+            }
+        }
+        if (row_nnz && tid == 0) row_nnz[row] = count;
+        __syncthreads();   // table clean, list consumed
+        if (tid == 0) s_count = 0;
+        // (the next row's first barrier -- after its staging -- orders this reset before any reservation)
+    }
+}
+
 // parts per listed row (sizes[n]: pad slot of the in-place exclusive scan)
 __global__ void split_parts_kernel(const int32_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ cnt, int64_t maxc,
                                    int64_t *__restrict__ sizes) {
@@ -819,6 +997,20 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             if (smem > 40 * 1024) CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH_NOTE(NUMERIC ? "spgemm_numeric_warp" : "spgemm_symbolic_warp");
             kern<<<(unsigned)((n + rpb - 1) / rpb), threads, smem, st>>>(sr, rows, n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox, a.mk);
+        } else if (b < NBINS - 1 && NUMERIC && !a.mk.Mp && n < ((int64_t)1 << 31) && opt_get_int("spgemm_rows", 1) != 0) {
+            // unmasked numeric rows: persistent CTAs, slot-list drain (spgemm_rows_kernel)
+            if constexpr (NUMERIC) {
+                const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
+                auto kern = spgemm_rows_kernel<SR, T, PACK>;
+                CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                int per_sm = 0;
+                CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+                if (per_sm < 1) per_sm = 1;
+                const long waves = std::max<long>(1, opt_get_int("spgemm_rows_waves", 1));
+                const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)g_num_sms * per_sm * waves);
+                LAUNCH_NOTE("spgemm_numeric_block");
+                kern<<<grid, threads, smem, st>>>(sr, rows, (int)n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
+            }
         } else if (b < NBINS - 1) {
             const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
             auto kern = spgemm_block_kernel<SR, T, NUMERIC, PACK, false>;
