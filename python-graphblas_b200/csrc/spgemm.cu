@@ -291,7 +291,7 @@ __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, 
 // ------------------------------------------------------------------ binning
 constexpr int NBINS = 13;   // 0: empty rows, 1-2: warp per row, 3-11: CTA per row (shared table), 12: global table
 constexpr int BIN_LAST_SHARED = NBINS - 2;
-struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int tf8[NBINS]; int flags; };
+struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int threads_rows[NBINS]; int tf8[NBINS]; int flags; };
 
 // shared memory of one CTA-per-row block beyond its hash table: per-thread staging of the A-row chunk
 static inline size_t block_stage_bytes(int threads, size_t val_bytes) {
@@ -304,6 +304,9 @@ static BinSpec make_bin_spec(size_t entry_bytes) {
     // small rows: narrow CTAs (a row has only a few products per thread; many independent CTAs per SM hide the dependent
     // load chain A -> Bp -> Bj of each row); big tables: occupancy is shared-memory bound, so more warps per CTA
     const int thr[NBINS] = {0, 256, 256, 64, 64, 128, 128, 256, 256, 512, 512, 1024, 1024};
+    // the persistent slot-list kernel (spgemm_rows_kernel) has no per-row clear / scan to amortise and prefers wider CTAs for the
+    // bigger tables: 40.3 -> 37.1 ms per scale-22 step with these (64 / 128-thread CTAs for the 512 / 1024 bins stay best)
+    const int thr_rows[NBINS] = {0, 256, 256, 64, 64, 256, 256, 512, 512, 1024, 1024, 1024, 1024};
     int maxcap = (int)((204 * 1024) / entry_bytes);   // 227 KB minus the chunk staging of 1024 threads and the static arrays
     maxcap -= maxcap % 256;
     const int tf_small = std::max(10, (int)opt_get_int("spgemm_table_factor8", 20));     // table = tf8/8 x count
@@ -312,11 +315,12 @@ static BinSpec make_bin_spec(size_t entry_bytes) {
     for (int b = 0; b < NBINS; b++) {
         s.cap[b] = caps[b];
         s.threads[b] = thr[b];
+        s.threads_rows[b] = thr_rows[b];
         s.tf8[b] = b >= big_from ? tf_big : tf_small;
         char key[32];
         snprintf(key, sizeof key, "spgemm_thr_%d", b);
         const long t = opt_get_int(key, 0);
-        if (b >= 3 && t >= 64 && t <= 1024 && t % 32 == 0) s.threads[b] = (int)t;
+        if (b >= 3 && t >= 64 && t <= 1024 && t % 32 == 0) s.threads[b] = s.threads_rows[b] = (int)t;
     }
     s.cap[BIN_LAST_SHARED] = maxcap > 16384 + 2048 ? maxcap : 16384;
     s.maxcount[0] = 0;
@@ -1000,13 +1004,14 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
         } else if (b < NBINS - 1 && NUMERIC && !a.mk.Mp && n < ((int64_t)1 << 31) && opt_get_int("spgemm_rows", 1) != 0) {
             // unmasked numeric rows: persistent CTAs, slot-list drain (spgemm_rows_kernel)
             if constexpr (NUMERIC) {
+                const int threads = bins.spec.threads_rows[b];
                 const size_t smem = (((size_t)cap * entry + 15) & ~(size_t)15) + block_stage_bytes(threads, sizeof(T));
                 auto kern = spgemm_rows_kernel<SR, T, PACK>;
                 CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 int per_sm = 0;
                 CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
                 if (per_sm < 1) per_sm = 1;
-                const long waves = std::max<long>(1, opt_get_int("spgemm_rows_waves", 1));
+                const long waves = std::max<long>(1, opt_get_int("spgemm_rows_waves", 2));   // CTAs queued beyond the resident ones even out the tail
                 const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)g_num_sms * per_sm * waves);
                 LAUNCH_NOTE("spgemm_numeric_block");
                 kern<<<grid, threads, smem, st>>>(sr, rows, (int)n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
