@@ -675,7 +675,7 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
     typedef HashTable<SR, T, true, PACK> Table;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_wsum[MAX_THREADS / 32];
-    __shared__ int s_count;
+    __shared__ int s_count[2];   // list length of the row in flight; the two slots alternate per row (see the end of the row loop)
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const size_t tbytes = (((size_t)cap * Table::entry_bytes() + 15) & ~(size_t)15);
     int64_t *s_bs = reinterpret_cast<int64_t *>(s_raw + tbytes);
@@ -687,10 +687,11 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
     Table tab;
     tab.bind(s_raw, (unsigned)cap, s_raw + (size_t)cap * 4, 1);
     tab.init(sr, tid, nthreads);   // the only full clear: every row's drain leaves the table empty again
-    if (tid == 0) s_count = 0;
+    if (tid == 0) { s_count[0] = 0; s_count[1] = 0; }
     __syncthreads();
 
-    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    int par = 0;
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x, par ^= 1) {
         const int64_t row = rows[r];
         tab.bind(s_raw, (unsigned)table_size_for(cnt[row], cap, tf8), s_raw + (size_t)cap * 4, 1);
         const int64_t ob = Op[row];
@@ -715,6 +716,7 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
             }
             if (wlane == 31) s_wsum[warp] = incl;
             __syncthreads();
+            if (tid == 0 && c0 == a_beg) s_count[par ^ 1] = 0;   // the previous row's list length: everybody has read it by now
             int base = 0;
             for (int w = 0; w < warp; w++) base += s_wsum[w];
             s_off[tid] = base + incl - len;
@@ -770,7 +772,7 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
                 }
                 if (total) {
                     int pos = 0;
-                    if (wlane == 0) pos = atomicAdd(&s_count, total);
+                    if (wlane == 0) pos = atomicAdd(&s_count[par], total);
                     pos = __shfl_sync(0xffffffffu, pos, 0);
 #pragma unroll
                     for (int u = 0; u < UNROLL; u++) {
@@ -781,28 +783,40 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
             }
             __syncthreads();   // s_* arrays are rewritten by the next chunk; after the last chunk: every insert and list store is done
         }
-        const int count = s_count;
+        const int count = s_count[par];
         // drain by the list: position i of the row's output receives the entry of slot list[i]; the slot is emptied
+        // (two list reads in flight per thread: they come back from L2, and 10 % of the samples sat on that load issued singly)
         T *lx = Ox + ob;
-        for (int i = tid; i < count; i += nthreads) {
-            const unsigned sl = (unsigned)lj[i];
-            if (Table::kPacked) {
-                const unsigned long long e = tab.ent[sl];
-                tab.ent[sl] = HASH_EMPTY64;
-                lj[i] = (int)(e >> 32);
-                lx[i] = unpack_value<T>(e);
-            } else {
-                lj[i] = tab.keys[sl];
-                lx[i] = tab.vals[sl];
-                tab.keys[sl] = HASH_EMPTY;
-                tab.vals[sl] = sr.identity();
+        for (int i0 = tid; i0 < count; i0 += 2 * nthreads) {
+            const int i1 = i0 + nthreads;
+            const unsigned sl0 = (unsigned)lj[i0];
+            const unsigned sl1 = i1 < count ? (unsigned)lj[i1] : 0u;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = u ? i1 : i0;
+                const unsigned sl = u ? sl1 : sl0;
+                if (i >= count) break;
+                if (Table::kPacked) {
+                    const unsigned long long e = tab.ent[sl];
+                    tab.ent[sl] = HASH_EMPTY64;
+                    lj[i] = (int)(e >> 32);
+                    lx[i] = unpack_value<T>(e);
+                } else {
+                    lj[i] = tab.keys[sl];
+                    lx[i] = tab.vals[sl];
+                    tab.keys[sl] = HASH_EMPTY;
+                    tab.vals[sl] = sr.identity();
+                }
             }
         }
         if (row_nnz && tid == 0) row_nnz[row] = count;
-        __syncthreads();   // table clean, list consumed
-        if (tid == 0) s_count = 0;
-        // (the next row's first barrier -- after its staging -- orders this reset before any reservation)
+        // No barrier here: the next row touches the table and the list counter only after the two barriers of its staging, and a
+        // thread reaches those only after its share of this drain.  The counter of THIS row is reset by thread 0 after the next
+        // row's first staging barrier (below), when every thread has read it; the next row counts in the other slot.
     }
+    // Tried and dropped: prefetching the next row's descriptor, A entries and B-row extents into registers while the current row
+    // is hashed (the four dependent round trips of a row's set-up, 12 % of the ncu samples).  It needs 21 more registers: at 53
+    // the 256-thread CTAs lose a third of their occupancy and the step went 37.7 -> 42.1 ms; capped at 40 registers 40.1 ms.
 }
 
 // parts per listed row (sizes[n]: pad slot of the in-place exclusive scan)
@@ -1011,7 +1025,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
                 int per_sm = 0;
                 CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
                 if (per_sm < 1) per_sm = 1;
-                const long waves = std::max<long>(1, opt_get_int("spgemm_rows_waves", 2));   // CTAs queued beyond the resident ones even out the tail
+                const long waves = std::max<long>(1, opt_get_int("spgemm_rows_waves", 4));   // CTAs queued beyond the resident ones even out the tail
                 const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)g_num_sms * per_sm * waves);
                 LAUNCH_NOTE("spgemm_numeric_block");
                 kern<<<grid, threads, smem, st>>>(sr, rows, (int)n, cap, bins.spec.tf8[b], a.cnt, a.Ap, a.Ae, a.Aj, (const T *)a.Ax, a.Bp, a.Be, a.Bj, (const T *)a.Bx, a.row_nnz, a.Op, a.Oj, (T *)a.Ox);
