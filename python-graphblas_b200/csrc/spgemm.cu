@@ -817,6 +817,7 @@ spgemm_rows_kernel(SR sr, const int32_t *__restrict__ rows, int n_rows, int cap,
     // Tried and dropped: prefetching the next row's descriptor, A entries and B-row extents into registers while the current row
     // is hashed (the four dependent round trips of a row's set-up, 12 % of the ncu samples).  It needs 21 more registers: at 53
     // the 256-thread CTAs lose a third of their occupancy and the step went 37.7 -> 42.1 ms; capped at 40 registers 40.1 ms.
+    // Also dropped: a single-barrier staging path for chunks of <= 32 A entries (warp 0's shuffle scan as the prefix): 35.8 -> 37.7 ms.
 }
 
 // parts per listed row (sizes[n]: pad slot of the in-place exclusive scan)
