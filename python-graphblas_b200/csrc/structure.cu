@@ -23,14 +23,15 @@ __global__ void check_sorted_kernel(int64_t nrows, const int64_t *__restrict__ p
 }
 
 // classify rows by length: <=32 handled in place by the warp kernel; medium rows and long rows are listed
-__global__ void sort_classify_kernel(int64_t nrows, const int64_t *__restrict__ ptr, int mid_cap, int big_cap,
-                                     int32_t *__restrict__ mid_rows, int32_t *__restrict__ big_rows,
+__global__ void sort_classify_kernel(int64_t nrows, const int64_t *__restrict__ ptr, int mid_cap, int mid2_cap, int big_cap,
+                                     int32_t *__restrict__ mid_rows, int32_t *__restrict__ mid2_rows, int32_t *__restrict__ big_rows,
                                      int32_t *__restrict__ huge_rows, unsigned int *__restrict__ counters) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     int64_t len = ptr[i + 1] - ptr[i];
     if (len <= 32) return;
     if (len <= mid_cap) mid_rows[atomicAdd(&counters[0], 1u)] = (int32_t)i;
+    else if (len <= mid2_cap) mid2_rows[atomicAdd(&counters[3], 1u)] = (int32_t)i;
     else if (len <= big_cap) big_rows[atomicAdd(&counters[1], 1u)] = (int32_t)i;
     else huge_rows[atomicAdd(&counters[2], 1u)] = (int32_t)i;
 }
@@ -217,17 +218,21 @@ template <typename V> static GrB_Info sort_huge_rows(GrB_Matrix A, const int32_t
 template <typename V> static GrB_Info sort_rows_typed(GrB_Matrix A) {
     std::string *err = &A->err;
     const int64_t nrows = A->nrows;
-    constexpr int MID_CAP = 512, BIG_CAP = 8192;
-    int32_t *mid = dev_alloc_t<int32_t>((size_t)nrows), *big = dev_alloc_t<int32_t>((size_t)nrows), *huge = dev_alloc_t<int32_t>((size_t)nrows);
+    // rows of 513 - 2048 entries get their own class: the bitonic network is a chain of barriers, so what it wants is many CTAs
+    // per SM, and a 16 KB CTA fits four times more often than the 64 KB one of the 8192 class (which took 166 of the 222 ms
+    // of sorting the 2.5 G-entry scale-22 product when it served all rows above 512)
+    constexpr int MID_CAP = 512, MID2_CAP = 2048, BIG_CAP = 8192;
+    int32_t *mid = dev_alloc_t<int32_t>((size_t)nrows), *mid2 = dev_alloc_t<int32_t>((size_t)nrows), *big = dev_alloc_t<int32_t>((size_t)nrows),
+            *huge = dev_alloc_t<int32_t>((size_t)nrows);
     unsigned int *counters = dev_alloc_t<unsigned int>(4);
-    if (!mid || !big || !huge || !counters) {
-        dev_free(mid); dev_free(big); dev_free(huge); dev_free(counters);
+    if (!mid || !mid2 || !big || !huge || !counters) {
+        dev_free(mid); dev_free(mid2); dev_free(big); dev_free(huge); dev_free(counters);
         return set_error(err, GrB_OUT_OF_MEMORY, "row sort lists");
     }
     cudaMemsetAsync(counters, 0, 16, g_stream);
     {
         LAUNCH_NOTE("sort_classify");
-        sort_classify_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, g_stream>>>(nrows, A->csr.ptr, MID_CAP, BIG_CAP, mid, big, huge, counters);
+        sort_classify_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, g_stream>>>(nrows, A->csr.ptr, MID_CAP, MID2_CAP, BIG_CAP, mid, mid2, big, huge, counters);
     }
     {
         int blocks = (int)std::min<int64_t>((nrows + 7) / 8, (int64_t)g_num_sms * 32);
@@ -242,6 +247,10 @@ template <typename V> static GrB_Info sort_rows_typed(GrB_Matrix A) {
         LAUNCH_NOTE("sort_rows_block512");
         sort_rows_block_kernel<V, MID_CAP, 128><<<h[0], 128, MID_CAP * 8, g_stream>>>(mid, A->csr.ptr, A->csr.idx, (V *)A->csr.val);
     }
+    if (h[3]) {
+        LAUNCH_NOTE("sort_rows_block2048");
+        sort_rows_block_kernel<V, MID2_CAP, 256><<<h[3], 256, MID2_CAP * 8, g_stream>>>(mid2, A->csr.ptr, A->csr.idx, (V *)A->csr.val);
+    }
     if (h[1]) {
         cudaFuncSetAttribute(sort_rows_block_kernel<V, BIG_CAP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_CAP * 8);
         LAUNCH_NOTE("sort_rows_block8192");
@@ -250,7 +259,7 @@ template <typename V> static GrB_Info sort_rows_typed(GrB_Matrix A) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) info = cuda_fail(err, e, "row sort");
     if (!info && h[2]) info = sort_huge_rows<V>(A, huge, (int64_t)h[2]);
-    dev_free(mid); dev_free(big); dev_free(huge); dev_free(counters);
+    dev_free(mid); dev_free(mid2); dev_free(big); dev_free(huge); dev_free(counters);
     return info;
 }
 
