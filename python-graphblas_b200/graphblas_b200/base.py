@@ -124,6 +124,56 @@ class Mask:
     def gb_name(self):
         return self.parent.name
 
+    # ---- mask algebra (reference core/mask.py:205-513: `m1 & m2`, `m1 | m2` give a new mask object).  The reference spells out
+    # 16 + 16 recipes; all of them follow from one model: a mask is (P, c) -- the set P of positions where its parent says
+    # "true" (the pattern for .S, the entries with a true value for .V) and whether it is complemented:
+    #   (P1,0) & (P2,0) = (P1 n P2, 0)   (P1,0) & (P2,1) = (P1 \ P2, 0)   (P1,1) & (P2,1) = (P1 u P2, 1)
+    #   (P1,0) | (P2,0) = (P1 u P2, 0)   (P1,0) | (P2,1) = (P2 \ P1, 1)   (P1,1) | (P2,1) = (P1 n P2, 1)
+    # and every set operation is ONE device call: n = eWiseMult(pair), u = eWiseAdd(pair), \ = one(P1) under the mask ~P2.S.
+    def _true_set(self):
+        """BOOL object whose PATTERN is the set of positions where the uncomplemented mask holds"""
+        from . import operator
+
+        par = self.parent
+        if self.structure:
+            return par
+        zero = False if par.dtype == BOOL else 0
+        return par.select(operator.select.valuene, zero).new()
+
+    def _combine(self, other, is_and):
+        from . import operator
+
+        if not isinstance(other, Mask):
+            raise TypeError(f"Invalid mask: {type(other)}")
+        if type(self.parent) is not type(other.parent) or self.parent.shape != other.parent.shape:
+            raise ValueError("masks can only be combined when their parents have the same kind and shape")
+        p1, p2, c1, c2 = self._true_set(), other._true_set(), self.complement, other.complement
+        pair, one = operator.binary.pair, operator.unary.one
+
+        def inter(a, b):
+            return a.ewise_mult(b, pair).new(BOOL)
+
+        def union(a, b):
+            return a.ewise_add(b, pair).new(BOOL)
+
+        def minus(a, b):
+            return a.apply(one).new(BOOL, mask=ComplementedStructuralMask(b))
+
+        if not c1 and not c2:
+            return StructuralMask(inter(p1, p2) if is_and else union(p1, p2))
+        if c1 and c2:
+            return ComplementedStructuralMask(union(p1, p2) if is_and else inter(p1, p2))
+        pos, neg = (p1, p2) if c2 else (p2, p1)          # pos: the uncomplemented operand, neg: the complemented one
+        if is_and:
+            return StructuralMask(minus(pos, neg))
+        return ComplementedStructuralMask(minus(neg, pos))
+
+    def __and__(self, other):
+        return self._combine(other, True)
+
+    def __or__(self, other):
+        return self._combine(other, False)
+
 
 class StructuralMask(Mask):
     structure = True
@@ -275,8 +325,8 @@ class Updater:
         self.parent._update(expr, **self.kwargs, opts=self.opts)
 
     def __setitem__(self, key, value):
-        # only `w(mask...)[:] = scalar` / `[...]` is on the path (GrB_Vector_assign_<T> with GrB_ALL)
-        if key not in (Ellipsis, slice(None)):
+        # only `w(mask...)[:] = scalar` / `[...]` / `C(mask...)[:, :] = scalar` is on the path (GrB_*_assign_<T> with GrB_ALL)
+        if key not in (Ellipsis, slice(None), (slice(None), slice(None))):
             raise NotImplementedError("only [:] assignment is supported by this backend")
         self.parent._update(self.parent._scalar_assign_expr(value), **self.kwargs, opts=self.opts)
 

@@ -218,7 +218,27 @@ class Matrix(BaseType):
                                 nrows=self._nrows, ncols=self._ncols, at=self._is_transposed)
 
     def _scalar_assign_expr(self, value):
-        raise NotImplementedError("scalar assignment into a Matrix is outside this backend's path")
+        """C(mask, accum, replace) << scalar -- GrB_Matrix_assign_<T> over GrB_ALL x GrB_ALL (reference core/matrix.py:3120-3180,
+        used by the mask-combination recipes core/mask.py:232-287).  Without a mask, or under a complemented one, the result is
+        a DENSE matrix: outside this backend's path.  Under a mask that names positions the call is a recipe over kernels that
+        exist: T = the scalar on the positions the mask allows (second(M, scalar) on the mask's pattern, for a value mask first
+        select(valuene 0)), then the ordinary masked write-back C<M, replace> accum= T."""
+        if isinstance(value, Scalar):
+            value = value.value
+        if value is None:
+            raise NotImplementedError("assigning an empty scalar (deleting entries) is outside this backend's path")
+        vt = _scalar_dtype(value)
+        nrows, ncols = self._nrows, self._ncols
+
+        def run(out, mask, accum, desc):
+            if mask is None or mask.complement:
+                raise NotImplementedError("a scalar assigned to every position (no mask, or a complemented one) makes the matrix "
+                                          "dense: outside this backend's path")
+            src = mask._true_set()
+            T = src.apply(operator.binary.second, right=value).new()
+            call("GrB_Matrix_apply", [out, mask, accum, operator.unary.identity[T.dtype], T, desc])
+
+        return MatrixExpression("assign", None, [], dtype=vt, nrows=nrows, ncols=ncols, custom=run)
 
     def ewise_add(self, other, op=None):
         """reference core/matrix.py:1972-2056 (union of the patterns)"""

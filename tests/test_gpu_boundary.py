@@ -262,3 +262,77 @@ def test_scipy_and_matrix_market_converters(gb, tmp_path):
     v = gb.Vector.from_coo([1, 4], [2.5, -1.0], size=6)
     col = gb.io.to_scipy_sparse(v)
     assert col.shape == (6, 1) and col[4, 0] == -1.0 and col.nnz == 2
+
+
+@pytest.mark.parametrize("kind", ["vector", "matrix"])
+def test_mask_algebra_and_matrix_scalar_assign(gb, kind):
+    """`m1 & m2`, `m1 | m2` for every pair of mask kinds (reference core/mask.py:205-513 lists 16 + 16 recipes; here one
+    set model, graphblas_b200/base.py Mask._combine), checked against numpy booleans by using the combined mask on a FULL source;
+    and `C(mask, accum, replace) << scalar` for a Matrix (GrB_Matrix_assign_<T> over GrB_ALL x GrB_ALL) against a dense model."""
+    rng = np.random.default_rng(21 if kind == "vector" else 22)
+    shape = (60,) if kind == "vector" else (9, 8)
+    size = int(np.prod(shape))
+
+    def random_obj(seed_density):
+        keep = rng.random(size) < seed_density
+        vals = rng.integers(0, 3, size)            # zeros among the stored values: .S and .V differ
+        flat = np.flatnonzero(keep)
+        if kind == "vector":
+            return gb.Vector.from_coo(flat, vals[flat], size=size), keep, vals != 0
+        return gb.Matrix.from_coo(flat // shape[1], flat % shape[1], vals[flat], nrows=shape[0], ncols=shape[1]), keep, vals != 0
+
+    def full_source():
+        v = np.arange(1, size + 1)
+        if kind == "vector":
+            return gb.Vector.from_coo(np.arange(size), v, size=size)
+        return gb.Matrix.from_coo(np.arange(size) // shape[1], np.arange(size) % shape[1], v, nrows=shape[0], ncols=shape[1])
+
+    def positions(obj):
+        if kind == "vector":
+            return set(obj.to_coo()[0].tolist())
+        I, J, _ = obj.to_coo()
+        return set((I.astype(np.int64) * shape[1] + J.astype(np.int64)).tolist())
+
+    a, a_keep, a_nz = random_obj(0.5)
+    b, b_keep, b_nz = random_obj(0.4)
+    src = full_source()
+    kinds = {"S": lambda o, keep, nz: (o.S, keep), "V": lambda o, keep, nz: (o.V, keep & nz),
+             "CS": lambda o, keep, nz: (~o.S, ~keep), "CV": lambda o, keep, nz: (~o.V, ~(keep & nz))}
+    for k1, f1 in kinds.items():
+        for k2, f2 in kinds.items():
+            m1, t1 = f1(a, a_keep, a_nz)
+            m2, t2 = f2(b, b_keep, b_nz)
+            for name, comb, want in (("and", m1 & m2, t1 & t2), ("or", m1 | m2, t1 | t2)):
+                out = type(src)(src.dtype, *shape) if kind == "matrix" else gb.Vector(src.dtype, size)
+                out(comb) << src
+                assert positions(out) == set(np.flatnonzero(want).tolist()), (kind, k1, k2, name)
+    if kind == "matrix":
+        # ---- scalar into a Matrix under a mask
+        C0, c_keep, _ = random_obj(0.3)
+        cI, cJ, cX = C0.to_coo()
+        dense = np.zeros(size, dtype=np.int64); have = np.zeros(size, dtype=bool)
+        dense[cI.astype(np.int64) * shape[1] + cJ.astype(np.int64)] = cX; have[cI.astype(np.int64) * shape[1] + cJ.astype(np.int64)] = True
+        for label, mask, mtrue, accum, replace in (("S", a.S, a_keep, None, False), ("V", a.V, a_keep & a_nz, None, False),
+                                                   ("S+accum", a.S, a_keep, "plus", False), ("V+replace", a.V, a_keep & a_nz, None, True)):
+            C = C0.dup()
+            kw = {"replace": True} if replace else {}
+            if accum:
+                C(mask, gb.binary.plus, **kw) << 7
+            else:
+                C(mask, **kw)[:, :] = 7
+            want_v = dense.copy(); want_h = have.copy()
+            if accum:
+                want_v[mtrue] = np.where(have[mtrue], dense[mtrue] + 7, 7)
+            else:
+                want_v[mtrue] = 7
+            want_h[mtrue] = True
+            if replace:
+                want_h[~mtrue] = False
+            I, J, X = C.to_coo()
+            flat = I.astype(np.int64) * shape[1] + J.astype(np.int64)
+            assert set(flat.tolist()) == set(np.flatnonzero(want_h).tolist()), label
+            assert np.array_equal(X, want_v[flat]), label
+        with pytest.raises(NotImplementedError):
+            C0.dup()(~a.S) << 1
+        with pytest.raises(NotImplementedError):
+            C0.dup() << 1
