@@ -314,6 +314,8 @@ GrB_Info GrB_cuda_Matrix_reduce(void *val, GrB_Type val_type, const GrB_BinaryOp
 /* v as an n x 1 matrix (column vector), built on the device: what Vector._as_matrix provides for Vector.inner / Vector.outer
    (reference graphblas/core/vector.py:193-209, 1715-1787) */
 GrB_Info GrB_cuda_Matrix_from_Vector(GrB_Matrix *A, const GrB_Vector v);
+/* C-API 2.0: C = square matrix of order size(v) + |k| with v on its k-th diagonal (reference graphblas/core/vector.py:627) */
+GrB_Info GrB_Matrix_diag(GrB_Matrix *C, const GrB_Vector v, int64_t k);
 GrB_Info GrB_cuda_Vector_device_arrays(const GrB_Vector v, void **vals, uint8_t **present);
 GrB_Info GrB_cuda_Vector_import_dense(GrB_Vector *v, GrB_Type type, GrB_Index n, const void *vals,
                                       const uint8_t *present /* NULL = full */, int on_device);

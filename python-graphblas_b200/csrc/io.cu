@@ -772,3 +772,58 @@ extern "C" GrB_Info GrB_cuda_Matrix_from_Vector(GrB_Matrix *Aout, const GrB_Vect
     *Aout = A;
     return GrB_SUCCESS;
 }
+
+// ------------------------------------------------------------------ GrB_Matrix_diag (reference core/vector.py:605-628: Vector.diag)
+__global__ void diag_counts_kernel(int64_t n, int64_t vn, int64_t roff, const uint8_t *__restrict__ present, int64_t *__restrict__ cnt) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; r <= n; r += s) {
+        const int64_t i = r - roff;
+        cnt[r] = (r < n && i >= 0 && i < vn && present[i]) ? 1 : 0;
+    }
+}
+__global__ void diag_fill_kernel(int64_t vn, int64_t roff, int64_t coff, const uint8_t *__restrict__ present,
+                                 const unsigned char *__restrict__ vals, size_t es, const int64_t *__restrict__ ptr,
+                                 int32_t *__restrict__ idx, unsigned char *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i < vn; i += s) {
+        if (!present[i]) continue;
+        const int64_t k = ptr[i + roff];
+        idx[k] = (int32_t)(i + coff);
+        for (size_t b = 0; b < es; b++) out[(size_t)k * es + b] = vals[(size_t)i * es + b];
+    }
+}
+// C = the (n + |k|) x (n + |k|) matrix with v on its k-th diagonal: v(i) at (i, i + k) for k >= 0, at (i - k, i) for k < 0
+extern "C" GrB_Info GrB_Matrix_diag(GrB_Matrix *C, const GrB_Vector v, int64_t k) {
+    CHECK_INIT();
+    if (!C) return GrB_NULL_POINTER;
+    if (!valid(v)) return GrB_UNINITIALIZED_OBJECT;
+    const int64_t n = v->n + (k < 0 ? -k : k);
+    if (n > (int64_t)INT32_MAX) return set_error(nullptr, GrB_NOT_IMPLEMENTED, "GrB_Matrix_diag: dimensions must be < 2^31");
+    GRB_TRY(vector_ensure_arrays(v));
+    GRB_TRY(vector_count(v));
+    GrB_Matrix A = nullptr;
+    GRB_TRY(matrix_new_shell(&A, v->type, n, n));
+    GrB_Info info = matrix_alloc_csr(A, v->nvals);
+    const int64_t roff = k < 0 ? -k : 0, coff = k > 0 ? k : 0;
+    if (!info) {
+        const int blocks = (int)std::min<int64_t>((n + 256) / 256, (int64_t)g_num_sms * 16);
+        note_launch("diag_counts");
+        diag_counts_kernel<<<blocks, 256, 0, g_stream>>>(n, v->n, roff, v->present, A->csr.ptr);
+        info = exclusive_scan_i64(A->csr.ptr, n + 1, &A->err);
+    }
+    if (!info && v->nvals > 0) {
+        const int blocks = (int)std::min<int64_t>((v->n + 255) / 256, (int64_t)g_num_sms * 16);
+        note_launch("diag_fill");
+        diag_fill_kernel<<<blocks, 256, 0, g_stream>>>(v->n, roff, coff, v->present, (const unsigned char *)v->vals, type_size(v->type),
+                                                       A->csr.ptr, A->csr.idx, (unsigned char *)A->csr.val);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) info = cuda_fail(&A->err, e, "GrB_Matrix_diag");
+    }
+    if (info) { set_last_error(A->err.c_str()); GrB_Matrix_free(&A); return info; }
+    A->nvals = v->nvals;
+    A->jumbled = false;
+    *C = A;
+    return GrB_SUCCESS;
+}

@@ -484,7 +484,55 @@ def _reduce_to_vector(self, op, method_name):
     return VectorExpression(method_name, "GrB_mxv", [self, ones], op=sr[op.type], size=self._nrows, at=self._is_transposed)
 
 
+def _ewise_broadcast(self, other, op, method_name, default_op):
+    """Matrix (op) Vector: the vector is broadcast along the rows (reference core/matrix.py:62-75, 1923-1940, 2014-2031).
+    ewise_mult: C = A (any).(op) diag(v) -- one GrB_mxm against the diagonal matrix of v, so C(i, j) = op(A(i, j), v(j)) wherever both
+    exist.  ewise_add: the union with the vector repeated in every row -- a dense nrows x ncols operand (0 (any).(second) v as an outer
+    product, built under the update's mask like the reference does), so only sensible for small or masked results."""
+    from .exceptions import DimensionMismatch
+
+    op = default_op if op is None else op
+    op = operator.get_typed_op(op, self.dtype, other.dtype, kind="binary")
+    if op.opclass == "Monoid":
+        op = op.binaryop
+    if op.opclass != "BinaryOp":
+        raise TypeError(f"{method_name} expects a BinaryOp or Monoid, got {op.opclass}")
+    if self._ncols != other._size:
+        raise DimensionMismatch(f"Dimensions not compatible for broadcasting Vector from the right to rows of Matrix in {method_name}.  "
+                                f"Matrix.ncols (={self._ncols}) must equal Vector.size (={other._size}).")
+    me = self
+
+    def run(out, mask, accum, desc):
+        if method_name == "ewise_mult":
+            sr = getattr(operator.semiring, f"any_{op.parent.name}", None)
+            if sr is None or op.type not in sr:
+                raise NotImplementedError(f"no builtin semiring any_{op.parent.name}[{op.type.name}] behind the broadcast {method_name}")
+            call("GrB_mxm", [out, mask, accum, sr[op.type], me._matrix if me._is_transposed else me, other.diag(),
+                             _with_transpose(desc, me._is_transposed)])
+        else:
+            full = Vector(other.dtype, me._nrows)
+            full[:] = 0
+            temp = full.outer(other, operator.binary.second).new(mask=mask) if (mask is not None and not mask.complement) else \
+                full.outer(other, operator.binary.second).new()
+            call("GrB_Matrix_eWiseAdd_BinaryOp", [out, mask, accum, op, me._matrix if me._is_transposed else me, temp,
+                                                  _with_transpose(desc, me._is_transposed)])
+
+    return MatrixExpression(method_name, None, [], dtype=op.return_type, nrows=self._nrows, ncols=self._ncols, custom=run)
+
+
+def _with_transpose(desc, at):
+    """the update's descriptor plus GrB_DESC_T0 when the matrix operand of a broadcast recipe is A.T"""
+    if not at:
+        return desc
+    from .base import descriptor_lookup
+
+    name = desc.name[len("GrB_DESC_"):] if desc is not None else ""
+    return descriptor_lookup(output_replace="R" in name, mask_structure="S" in name, mask_complement="C" in name, transpose_first=True)
+
+
 def _ewise(self, other, op, method_name, cfunc, default_op):
+    if isinstance(other, Vector):
+        return _ewise_broadcast(self, other, op, method_name, default_op)
     if not isinstance(other, (Matrix, TransposedMatrix)):
         raise TypeError(f"{method_name} expects a Matrix, got {type(other).__name__}")
     op = default_op if op is None else op

@@ -239,6 +239,18 @@ class Vector(BaseType):
         call("GrB_cuda_Matrix_from_Vector", [ctypes.byref(h), self])
         return out
 
+    def diag(self, k=0, *, name=None):
+        """reference core/vector.py:605-628: the square Matrix of order size + |k| with this vector on its k-th diagonal
+        (one C call: GrB_Matrix_diag)"""
+        from .matrix import Matrix
+
+        k = int(k)
+        n = self._size + abs(k)
+        h = ctypes.c_void_p()
+        out = Matrix._from_handle(h, self.dtype, n, n, name)
+        call("GrB_Matrix_diag", [ctypes.byref(h), self, ctypes.c_int64(k)])
+        return out
+
     def inner(self, other, op=None):
         """reference core/vector.py:1715-1744: s = v' (+).(x) w, run as GrB_vxm against w cast to an n x 1 matrix; the result is
         a Scalar (empty when no index is shared)."""

@@ -336,3 +336,47 @@ def test_mask_algebra_and_matrix_scalar_assign(gb, kind):
             C0.dup()(~a.S) << 1
         with pytest.raises(NotImplementedError):
             C0.dup() << 1
+
+
+def test_vector_diag_and_matrix_vector_broadcast(gb):
+    """Vector.diag (GrB_Matrix_diag, reference core/vector.py:605-628) and the broadcast recipes built on it: A.ewise_mult(v) =
+    A (any).(op) diag(v) -- a caller of GrB_mxm -- and A.ewise_add(v) (reference core/matrix.py:62-75); against dense numpy models."""
+    rng = np.random.default_rng(31)
+    m, n = 13, 11
+    keep = rng.random((m, n)) < 0.4
+    Ad = rng.integers(1, 9, (m, n)).astype(np.int64)
+    I, J = np.nonzero(keep)
+    A = gb.Matrix.from_coo(I, J, Ad[I, J], nrows=m, ncols=n)
+    vkeep = rng.random(n) < 0.6
+    vd = rng.integers(1, 9, n).astype(np.int64)
+    v = gb.Vector.from_coo(np.flatnonzero(vkeep), vd[vkeep], size=n)
+    # ---- diag, every offset
+    for k in (0, 2, -3):
+        D = v.diag(k)
+        assert D.shape == (n + abs(k), n + abs(k)) and D.nvals == int(vkeep.sum())
+        di, dj, dx = D.to_coo()
+        idx = np.flatnonzero(vkeep)
+        assert np.array_equal(di, idx + max(-k, 0)) and np.array_equal(dj, idx + max(k, 0)) and np.array_equal(dx, vd[vkeep])
+    # ---- ewise_mult broadcast: intersection of A's pattern with the columns v holds
+    for opname, f in (("times", lambda a, b: a * b), ("plus", lambda a, b: a + b), ("first", lambda a, b: a), ("minus", lambda a, b: a - b)):
+        C = A.ewise_mult(v, getattr(gb.binary, opname)).new()
+        ci, cj, cx = C.to_coo()
+        want = keep & vkeep[None, :]
+        wi, wj = np.nonzero(want)
+        assert np.array_equal(ci, wi) and np.array_equal(cj, wj), opname
+        assert np.array_equal(cx, f(Ad, vd[None, :])[wi, wj]), opname
+    # the transposed operand
+    Ct = A.T.ewise_mult(gb.Vector.from_coo(np.arange(m), np.arange(1, m + 1), size=m), gb.binary.times).new()
+    ti, tj, tx = Ct.to_coo()
+    wi, wj = np.nonzero(keep.T)
+    assert np.array_equal(ti, wi) and np.array_equal(tj, wj) and np.array_equal(tx, (Ad.T * np.arange(1, m + 1)[None, :])[wi, wj])
+    # ---- ewise_add broadcast: union of A's pattern with v repeated in every row
+    C = A.ewise_add(v, gb.binary.plus).new()
+    ci, cj, cx = C.to_coo()
+    want = keep | vkeep[None, :]
+    wi, wj = np.nonzero(want)
+    assert np.array_equal(ci, wi) and np.array_equal(cj, wj)
+    dense = np.where(keep, Ad, 0) + np.where(vkeep[None, :], vd[None, :], 0)
+    assert np.array_equal(cx, dense[wi, wj])
+    with pytest.raises(gb.exceptions.DimensionMismatch):
+        A.ewise_mult(gb.Vector(gb.dtypes.INT64, n + 1))
