@@ -11,13 +11,10 @@
 
 extern "C" const GrB_Index *GrB_ALL;
 
-static bool semiring_supported(const GrB_Semiring op) {
-    if (!op) return false;
-    switch (op->mul) {
-        case OP_EQ: case OP_NE: case OP_GT: case OP_LT: case OP_GE: case OP_LE: return false;
-        default: return true;
-    }
-}
+// Every builtin semiring this library exports has kernels: multiplies that return their operand type run as they are, comparison
+// multiplies (GxB_LOR_GT_INT32 ...) run in the operand type with the comparison as 1 / 0 and the logical monoid mapped onto it
+// (csrc/gen_builtins.py), the result cast by the write-back.
+static bool semiring_supported(const GrB_Semiring op) { return op != nullptr; }
 
 
 // shared tail of GrB_mxv / GrB_vxm: multiply (with the write-back fused into the kernel when possible), then write back

@@ -42,12 +42,15 @@ for t in ["FP32", "FP64"]:   # the floating-point GxB unary ops the aggregator f
 GRB_BIN = ["FIRST", "SECOND", "MIN", "MAX", "PLUS", "MINUS", "TIMES", "DIV"]
 GXB_BIN = ["RMINUS", "RDIV", "PAIR", "ANY", "LOR", "LAND", "LXOR", "ISEQ", "ISNE", "POW"]
 CMP = ["EQ", "NE", "GT", "LT", "GE", "LE"]
+IS_CMP = {"ISGT": "GT", "ISLT": "LT", "ISGE": "GE", "ISLE": "LE"}
 for t in TYPES:
     for op in GRB_BIN:
         emit("GrB_BinaryOp", f"GrB_{op}_{t}", f'{{OP_{op}, TC_{t}, TC_{t}, "GrB_{op}_{t}"}}')
     emit("GrB_BinaryOp", f"GrB_ONEB_{t}", f'{{OP_PAIR, TC_{t}, TC_{t}, "GrB_ONEB_{t}"}}')
     for op in GXB_BIN:
         emit("GrB_BinaryOp", f"GxB_{op}_{t}", f'{{OP_{op}, TC_{t}, TC_{t}, "GxB_{op}_{t}"}}')
+    for op, code in IS_CMP.items():   # GxB_ISGT ...: the comparison as 1 / 0 in the operand type (same device code as GT ..., other result type)
+        emit("GrB_BinaryOp", f"GxB_{op}_{t}", f'{{OP_{code}, TC_{t}, TC_{t}, "GxB_{op}_{t}"}}')
     for op in CMP:
         emit("GrB_BinaryOp", f"GrB_{op}_{t}", f'{{OP_{op}, TC_{t}, TC_BOOL, "GrB_{op}_{t}"}}')
 for op in ["LOR", "LAND", "LXOR", "LXNOR"]:
@@ -75,8 +78,17 @@ for t in NUM:
                 emit("GrB_Semiring", f"GrB_{a}_{m}_SEMIRING_{t}", f'{{OP_{a}, OP_{m}, TC_{t}, "GrB_{a}_{m}_SEMIRING_{t}"}}')
             else:
                 emit("GrB_Semiring", f"GxB_{a}_{m}_{t}", f'{{OP_{a}, OP_{m}, TC_{t}, "GxB_{a}_{m}_{t}"}}')
+        for m, code in IS_CMP.items():
+            emit("GrB_Semiring", f"GxB_{a}_{m}_{t}", f'{{OP_{a}, OP_{code}, TC_{t}, "GxB_{a}_{m}_{t}"}}')
+# comparison multiplies under a logical monoid (GxB_LOR_GT_INT32 ...: T x T -> BOOL, monoid over BOOL).  The kernels are typed by ONE
+# type, so these run in T: the comparison yields 1 / 0 in T, LOR of booleans is MAX of those, LAND is MIN, ANY is ANY; the write-back
+# casts the 1 / 0 result into the output type (BOOL for `.new()`).  LXOR / EQ monoids would need the parity of a sum: not offered.
+for t in NUM:
+    for a, acode in (("LOR", "OP_MAX"), ("LAND", "OP_MIN"), ("ANY", "OP_ANY")):
+        for m in CMP:
+            emit("GrB_Semiring", f"GxB_{a}_{m}_{t}", f'{{{acode}, OP_{m}, TC_{t}, "GxB_{a}_{m}_{t}"}}')
 BADDS = {"LOR": "OP_LOR", "LAND": "OP_LAND", "LXOR": "OP_LXOR", "EQ": "OP_LXNOR", "ANY": "OP_ANY"}
-BMULS = ["FIRST", "SECOND", "PAIR", "LOR", "LAND", "LXOR"]
+BMULS = ["FIRST", "SECOND", "PAIR", "LOR", "LAND", "LXOR", "EQ", "NE", "GT", "LT", "GE", "LE"]
 GRB_BSR = {("LOR", "LAND"): "GrB_LOR_LAND_SEMIRING_BOOL", ("LAND", "LOR"): "GrB_LAND_LOR_SEMIRING_BOOL",
            ("LXOR", "LAND"): "GrB_LXOR_LAND_SEMIRING_BOOL", ("EQ", "LOR"): "GrB_LXNOR_LOR_SEMIRING_BOOL"}
 for a, acode in BADDS.items():

@@ -653,6 +653,10 @@ template <typename T> static GrB_Info mat_vec_typed(const MatVecArgs &a) {
             case OP_RDIV: mul = OP_DIV; break;
             case OP_POW: mul = OP_RPOW; break;
             case OP_RPOW: mul = OP_POW; break;
+            case OP_GT: mul = OP_LT; break;
+            case OP_LT: mul = OP_GT; break;
+            case OP_GE: mul = OP_LE; break;
+            case OP_LE: mul = OP_GE; break;
             default: break;   // commutative multiplies
         }
     }

@@ -158,7 +158,7 @@ def initialize():
     re_mon_grb = re.compile(rf"^GrB_(PLUS|TIMES|MIN|MAX|LOR|LAND|LXOR|LXNOR)_MONOID_({_TYPES})$")
     re_mon_gxb = re.compile(rf"^GxB_(ANY|EQ)_({_TYPES})_MONOID$")
     re_bin = re.compile(rf"^G[rx]B_(FIRST|SECOND|ONEB|PAIR|MIN|MAX|PLUS|MINUS|RMINUS|TIMES|DIV|RDIV|ANY|LOR|LAND|LXOR|"
-                        rf"ISEQ|ISNE|POW|EQ|NE|GT|LT|GE|LE)_({_TYPES})$")
+                        rf"ISEQ|ISNE|ISGT|ISLT|ISGE|ISLE|POW|EQ|NE|GT|LT|GE|LE)_({_TYPES})$")
     re_bin_bool = re.compile(r"^GrB_(LOR|LAND|LXOR|LXNOR)$")
     re_un = re.compile(rf"^G[rx]B_(IDENTITY|AINV|MINV|ABS|ONE|LNOT|BNOT|SQRT|EXP|LOG|EXP2|LOG2|LOG10|FLOOR|CEIL|ROUND|TRUNC|SIGNUM)_({_TYPES})$")
     re_sel_pos = re.compile(r"^GrB_(TRIL|TRIU|DIAG|OFFDIAG|COLLE|COLGT|ROWLE|ROWGT)$")
@@ -174,7 +174,8 @@ def initialize():
             op = _get(semiring, Semiring, f"{add}_{mul}")
             dt = lookup_dtype(t)
             if dt not in op._typed_ops or n.startswith("GrB_"):
-                op._add(TypedOp(op, op.name, dt, dt, getattr(L, n), n, "Semiring"))
+                ret = BOOL if mul in ("eq", "ne", "gt", "lt", "ge", "le") else dt   # comparison multiplies: T x T -> BOOL
+                op._add(TypedOp(op, op.name, dt, ret, getattr(L, n), n, "Semiring"))
             semiring_names.add(op.name)
             continue
         m = re_mon_grb.match(n) or re_mon_gxb.match(n)

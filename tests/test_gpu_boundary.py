@@ -380,3 +380,56 @@ def test_vector_diag_and_matrix_vector_broadcast(gb):
     assert np.array_equal(cx, dense[wi, wj])
     with pytest.raises(gb.exceptions.DimensionMismatch):
         A.ewise_mult(gb.Vector(gb.dtypes.INT64, n + 1))
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.float64, np.bool_, np.uint8], ids=lambda d: np.dtype(d).name)
+def test_comparison_multiply_semirings(gb, dtype):
+    """GxB_{LOR,LAND,ANY}_{EQ,NE,GT,LT,GE,LE}_<T>: the multiply compares (T x T -> BOOL), the monoid is logical.  The kernels run them
+    in T (comparison as 1 / 0, LOR = max, LAND = min; csrc/gen_builtins.py) and the write-back casts to BOOL; checked for mxm, mxv
+    and vxm against a dense numpy model over the shared indices k."""
+    rng = np.random.default_rng(abs(hash(("cmp", np.dtype(dtype).name))) % 2**32)
+    m, k, n = 17, 23, 14
+    def rnd(r, c, dens):
+        keep = rng.random((r, c)) < dens
+        vals = (rng.integers(0, 2, (r, c)) if dtype == np.bool_ else rng.integers(0, 4, (r, c))).astype(dtype)
+        return keep, vals
+    ak, av = rnd(m, k, 0.4)
+    bk, bv = rnd(k, n, 0.4)
+    ai, aj = np.nonzero(ak); bi, bj = np.nonzero(bk)
+    A = gb.Matrix.from_coo(ai, aj, av[ai, aj], nrows=m, ncols=k)
+    B = gb.Matrix.from_coo(bi, bj, bv[bi, bj], nrows=k, ncols=n)
+    cmpf = {"eq": np.equal, "ne": np.not_equal, "gt": np.greater, "lt": np.less, "ge": np.greater_equal, "le": np.less_equal}
+    for add in ("lor", "land", "any"):
+        for mul, f in cmpf.items():
+            sr = getattr(gb.semiring, f"{add}_{mul}")
+            C = A.mxm(B, sr).new()
+            assert C.dtype == gb.dtypes.BOOL, (add, mul, C.dtype)
+            ci, cj, cx = C.to_coo()
+            both = ak[:, :, None] & bk[None, :, :]                      # (i, k, j): A(i,k) and B(k,j) both present
+            prod = f(av[:, :, None], bv[None, :, :])
+            pattern = both.any(axis=1)
+            wi, wj = np.nonzero(pattern)
+            assert np.array_equal(ci, wi) and np.array_equal(cj, wj), (add, mul)
+            if add == "lor":
+                want = (both & prod).any(axis=1)
+                assert np.array_equal(cx, want[wi, wj]), (add, mul)
+            elif add == "land":
+                want = (~both | prod).all(axis=1)
+                assert np.array_equal(cx, want[wi, wj]), (add, mul)
+            else:   # any: some product's value
+                lo, hi = (both & prod).any(axis=1), (~both | prod).all(axis=1)   # True is possible / False is impossible
+                assert np.all((cx <= lo[wi, wj]) & (cx >= hi[wi, wj])), (add, mul)
+    # vectors: mxv and vxm with lor_gt
+    xk = rng.random(k) < 0.6
+    xv = rng.integers(0, 4, k).astype(dtype) if dtype != np.bool_ else rng.integers(0, 2, k).astype(dtype)
+    x = gb.Vector.from_coo(np.flatnonzero(xk), xv[xk], size=k)
+    w = A.mxv(x, gb.semiring.lor_gt).new()
+    wi_, wx = w.to_coo()
+    both = ak & xk[None, :]
+    assert np.array_equal(wi_, np.flatnonzero(both.any(axis=1)))
+    assert np.array_equal(wx, (both & (av > xv[None, :])).any(axis=1)[wi_])
+    w2 = x.vxm(B, gb.semiring.land_le).new()
+    w2i, w2x = w2.to_coo()
+    both = xk[:, None] & bk
+    assert np.array_equal(w2i, np.flatnonzero(both.any(axis=0)))
+    assert np.array_equal(w2x, (~both | (xv[:, None] <= bv)).all(axis=0)[w2i])
