@@ -657,12 +657,15 @@ def run_ours(args):
         check = checksum()
         ms_e2e, wall_e2e = time_e2e(args.e2e_blocks)
         check2 = checksum()
-        e2e = {"value": nnz_c / (ms_e2e * 1e-3), "unit": "nnz-out/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "wall_ms_per_step": wall_e2e,
-               "api": f"GrB_cuda_Matrix_import_csr32, then graphblas_b200.cuda.mxm_to_host_csr32: GrB_mxm on {args.e2e_blocks} row blocks, each exported "
-                      "with GrB_cuda_Matrix_export_csr32_async while the next is multiplied (int32 column indices, pinned host buffers)",
-               "single_call": {"ms_per_step": ms_single, "value": nnz_c / (ms_single * 1e-3),
-                               "api": "GrB_cuda_Matrix_import_csr32 / one GrB_mxm / GrB_cuda_Matrix_export_csr32"},
+        api_single = "GrB_cuda_Matrix_import_csr32 / one GrB_mxm / GrB_cuda_Matrix_export_csr32 (int32 column indices, pinned host buffers)"
+        api_blocks = (f"GrB_cuda_Matrix_import_csr32, then graphblas_b200.cuda.mxm_to_host_csr32: GrB_mxm on {args.e2e_blocks} row blocks, each exported "
+                      "with GrB_cuda_Matrix_export_csr32_async while the next is multiplied (int32 column indices, pinned host buffers)")
+        # both are calls a user can make; the headline is the faster one (the D2H of the 20 GB result at PCIe speed bounds either)
+        best_ms, best_api = (ms_single, api_single) if ms_single <= ms_e2e else (ms_e2e, api_blocks)
+        e2e = {"value": nnz_c / (best_ms * 1e-3), "unit": "nnz-out/s", "ms_per_step": best_ms,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": best_api,
+               "variants": {"single_call": {"ms_per_step": ms_single, "value": nnz_c / (ms_single * 1e-3), "api": api_single},
+                            "row_blocks_overlapped": {"ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e, "value": nnz_c / (ms_e2e * 1e-3), "api": api_blocks}},
                "same_result": check == check2 if world == 1 else None}
         del h_ptr, h_col, h_val, o_ptr, o_col, o_val
         # (2) what the reference's Matrix.from_csr / to_csr hand over (graphblas/core/matrix.py:992-1068, 1601-1645): uint64 index
