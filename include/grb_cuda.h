@@ -292,6 +292,10 @@ GrB_Info GrB_cuda_Matrix_export_csr32(int64_t *Ap, int32_t *Aj, void *Ax, GrB_In
                                       GrB_Matrix A, int sort);
 /* the same copies on a separate copy stream, ordered after the work enqueued so far: the D2H of one result overlaps the
  * computation of the next.  Host arrays (pinned) and the matrix must stay alive until GrB_cuda_copy_sync() returns. */
+/* fence on the copy stream: the ticket names everything enqueued so far; copy_wait(ticket) returns when that has drained while later
+   copies keep running (release the source of block k while block k + 1 is still leaving the device); at most 16 tickets outstanding */
+GrB_Info GrB_cuda_copy_fence(int *ticket);
+GrB_Info GrB_cuda_copy_wait(int ticket);
 GrB_Info GrB_cuda_Matrix_export_csr32_async(int64_t *Ap, int32_t *Aj, void *Ax, GrB_Index nvals_capacity, GrB_Matrix A);
 GrB_Info GrB_cuda_copy_sync(void);
 /* raw device views (valid until the object is next modified) */

@@ -356,6 +356,30 @@ extern "C" GrB_Info GrB_cuda_copy_sync(void) {
     if (g_copy_stream) CUDA_TRY(nullptr, cudaStreamSynchronize(g_copy_stream));
     return GrB_SUCCESS;
 }
+// A fence on the copy stream: *ticket names everything enqueued on it so far; GrB_cuda_copy_wait(ticket) returns when that has
+// drained, while LATER copies keep running -- so the caller can release the source of copy k while copy k + 1 is in flight.
+constexpr int COPY_FENCES = 16;
+static cudaEvent_t g_copy_fence[COPY_FENCES];
+static bool g_copy_fence_init = false;
+static int g_copy_fence_next = 0;
+extern "C" GrB_Info GrB_cuda_copy_fence(int *ticket) {
+    if (!ticket) return GrB_NULL_POINTER;
+    if (!g_copy_stream) { *ticket = -1; return GrB_SUCCESS; }
+    if (!g_copy_fence_init) {
+        for (int q = 0; q < COPY_FENCES; q++) CUDA_TRY(nullptr, cudaEventCreateWithFlags(&g_copy_fence[q], cudaEventDisableTiming));
+        g_copy_fence_init = true;
+    }
+    const int t = g_copy_fence_next;
+    g_copy_fence_next = (g_copy_fence_next + 1) % COPY_FENCES;
+    CUDA_TRY(nullptr, cudaEventRecord(g_copy_fence[t], g_copy_stream));
+    *ticket = t;
+    return GrB_SUCCESS;
+}
+extern "C" GrB_Info GrB_cuda_copy_wait(int ticket) {
+    if (ticket < 0 || ticket >= COPY_FENCES || !g_copy_fence_init) return GrB_SUCCESS;
+    CUDA_TRY(nullptr, cudaEventSynchronize(g_copy_fence[ticket]));
+    return GrB_SUCCESS;
+}
 
 extern "C" GrB_Info GrB_cuda_Matrix_extractTuples(GrB_Index *I, GrB_Index *J, void *X, GrB_Type xtype, GrB_Index *nvals,
                                                   const GrB_Matrix A) {

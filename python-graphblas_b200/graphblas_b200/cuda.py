@@ -151,8 +151,9 @@ def mxm_to_host_csr32(A, B, semiring, out_indptr, out_cols, out_vals, *, blocks=
     bounds[0], bounds[-1] = 0, m
     for k in range(1, len(bounds)):
         bounds[k] = max(bounds[k], bounds[k - 1])
-    keep, offs = [], []
+    offs = []
     off = 0
+    prev = None   # (block result, copy-stream ticket) of the block that is leaving the device
     for q0, q1 in zip(bounds[:-1], bounds[1:]):
         if q1 == q0:
             continue
@@ -164,10 +165,15 @@ def mxm_to_host_csr32(A, B, semiring, out_indptr, out_cols, out_vals, *, blocks=
             copy_sync()
             raise ValueError(f"output arrays too small: need more than {out_cols.shape[0]} entries")
         matrix_export_host_csr32_async(Cb, out_indptr[q0:q1 + 1], out_cols[off:off + nv], out_vals[off:off + nv])
-        keep.append(Cb)
+        t = ctypes.c_int(-1)
+        call("GrB_cuda_copy_fence", [ctypes.byref(t)])
+        if prev is not None:   # the previous block has (nearly) drained while this one was multiplied: release it, two blocks alive at most
+            call("GrB_cuda_copy_wait", [ctypes.c_int(prev[1])])
+        prev = (Cb, t.value)
         offs.append((q0, q1, off))
         off += nv
     copy_sync()
+    prev = None
     for q0, q1, o in offs:   # block-local row pointers -> global ones
         if o:
             out_indptr[q0:q1] += o
