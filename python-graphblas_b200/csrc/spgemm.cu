@@ -291,7 +291,8 @@ __global__ void row_flops_kernel(int64_t nrows, const int64_t *__restrict__ Ap, 
 // ------------------------------------------------------------------ binning
 constexpr int NBINS = 13;   // 0: empty rows, 1-2: warp per row, 3-11: CTA per row (shared table), 12: global table
 constexpr int BIN_LAST_SHARED = NBINS - 2;
-struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int threads_rows[NBINS]; int tf8[NBINS]; int flags; };
+struct BinSpec { int64_t maxcount[NBINS]; int cap[NBINS]; int threads[NBINS]; int threads_rows[NBINS]; int tf8[NBINS]; int flags;
+                 int64_t split_keys; /* keys a part of a split row is sized for (its table is the largest shared one) */ };
 
 // shared memory of one CTA-per-row block beyond its hash table: per-thread staging of the A-row chunk
 static inline size_t block_stage_bytes(int threads, size_t val_bytes) {
@@ -329,6 +330,10 @@ static BinSpec make_bin_spec(size_t entry_bytes) {
         if (s.maxcount[b] < s.maxcount[b - 1]) s.maxcount[b] = s.maxcount[b - 1];   // a tighter factor must not reorder the bins
     }
     s.maxcount[NBINS - 1] = INT64_MAX;
+    // a part of a split row fills its table to about split_load8 / 8 / 1.125 = 0.56: fewer parts mean fewer CTAs that each re-read
+    // the whole row (measured: 3.59 ms at the bins' own 0.4, 3.32 at 0.44, 3.05 at 0.56); parts_of() keeps 1/8 head-room for the
+    // imbalance of the hash split, and the insert traps rather than spins should a table ever fill up
+    s.split_keys = ((int64_t)s.cap[BIN_LAST_SHARED] * std::min<long>(6, std::max<long>(2, opt_get_int("spgemm_split_load8", 5)))) / 8;
     s.flags = opt_get_int("spgemm_cas_first", 1) != 0 ? 1 : 0;
     return s;
 }
@@ -355,7 +360,7 @@ __global__ void bin_count_kernel(BinSpec spec, int64_t nrows, const int64_t *__r
         atomicAdd(&s[b], 1u);
         if (b == NBINS - 1) {
             atomicAdd(&s_g, (unsigned long long)gtable_size_of(c));
-            atomicAdd(&s_p, (unsigned long long)parts_of(c, spec.maxcount[BIN_LAST_SHARED]));
+            atomicAdd(&s_p, (unsigned long long)parts_of(c, spec.split_keys));
         }
     }
     __syncthreads();
@@ -1041,7 +1046,7 @@ static GrB_Info run_bins(const SR &sr, const Bins &bins, const HashArgs &a, std:
             // rows whose bound exceeds the largest shared table: global-memory tables.  The total table size came back with the
             // bin counts, so the usual case is fully asynchronous: sizes -> device scan -> one launch, no host round trip
             // unmasked products with exact-count output (row_nnz): split every such row over several CTAs with shared tables
-            const int64_t maxc = bins.spec.maxcount[BIN_LAST_SHARED];
+            const int64_t maxc = bins.spec.split_keys;
             if (!a.mk.Mp && a.row_nnz && bins.split_parts > 0 && bins.split_parts < ((unsigned long long)1 << 31) && n < ((int64_t)1 << 31) &&
                 opt_get_int("spgemm_split", 1) != 0) {
                 int64_t *poffs = dev_alloc_t<int64_t>((size_t)n + 1);

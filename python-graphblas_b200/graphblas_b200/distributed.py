@@ -29,15 +29,15 @@ def row_blocks_by_prefix(prefix, world):
     return [int(b) for b in np.maximum.accumulate(bounds)]
 
 
-def mxm_row_costs(rowflops, *, split_above=10440, reread=0.5):
+def mxm_row_costs(rowflops, *, split_above=10440, part_keys=16320, reread=1.0):
     """Per-row cost estimate of the hash SpGEMM for the row partition of A: the flop bound, except that a row too big for one
-    shared-memory table is hashed by ceil(1.125 flops / split_above) CTAs which ALL stream the row's products (csrc/spgemm.cu,
+    shared-memory table is hashed by ceil(1.125 flops / part_keys) CTAs which ALL stream the row's products (csrc/spgemm.cu,
     split rows) -- its cost grows by `reread` per extra part.  Balancing this instead of the plain flops keeps the rank that
     owns the heavy low-index rows of an R-MAT matrix from finishing last: slowest / mean block time of the 8-way split at scale 22 is
-    1.12 with plain flops, 1.06 at reread = 0.25, 1.01 at 0.5, 1.03 at 1.0 (scripts/part_balance.py, one B200).
+    1.13 with plain flops, 1.04 at reread = 0.5, 1.03 at 1.0, 1.08 at 2.0 (scripts/part_balance.py, one B200).
     `rowflops`: torch tensor or numpy array; returns the same kind (float64)."""
     f = rowflops.double() if hasattr(rowflops, "double") else np.asarray(rowflops, dtype=np.float64)
-    parts = (f * 1.125 / split_above).ceil() if hasattr(f, "ceil") else np.ceil(f * 1.125 / split_above)
+    parts = (f * 1.125 / part_keys).ceil() if hasattr(f, "ceil") else np.ceil(f * 1.125 / part_keys)
     extra = (parts - 1).clamp(min=0) if hasattr(parts, "clamp") else np.maximum(parts - 1, 0)
     extra = extra * (f > split_above)   # rows that fit one table are not split at all
     return f * (1.0 + reread * extra)
