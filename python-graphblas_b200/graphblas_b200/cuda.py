@@ -181,6 +181,40 @@ def mxm_to_host_csr32(A, B, semiring, out_indptr, out_cols, out_vals, *, blocks=
     return off
 
 
+# ------------------------------------------------------------------ DLPack (any array library that speaks it -- CuPy, JAX, RAPIDS ...)
+def vector_to_dlpack(v, sync=True):
+    """(values, present) of the vector as DLPack capsules over the library's own device arrays (zero-copy; valid until v changes)"""
+    from torch.utils.dlpack import to_dlpack
+
+    vals, present = vector_as_torch(v, sync=sync)
+    return to_dlpack(vals), to_dlpack(present)
+
+
+def vector_from_dlpack(values, present=None, *, name=None):
+    """a Vector from DLPack capsules / objects with __dlpack__ (dense values + optional uint8 presence; copied onto the library's arrays)"""
+    import torch
+
+    vals = torch.from_dlpack(values)
+    pres = None if present is None else torch.from_dlpack(present)
+    return vector_from_torch(vals, pres, name=name)
+
+
+def matrix_to_dlpack(A, sync=True):
+    """(indptr int64, col_indices int32, values) of the matrix's device CSR as DLPack capsules (zero-copy, read-only; rows may be
+    unsorted after mxm -- matrix_sort(A) first when order matters)"""
+    from torch.utils.dlpack import to_dlpack
+
+    return tuple(to_dlpack(t) for t in matrix_as_torch(A, sync=sync))
+
+
+def matrix_from_dlpack(indptr, col_indices, values, nrows, ncols, *, sorted=True, name=None):
+    """a Matrix from DLPack capsules / objects of a device CSR (indptr int64, col_indices int32, values; copied)"""
+    import torch
+
+    return matrix_from_device_csr(torch.from_dlpack(indptr), torch.from_dlpack(col_indices), torch.from_dlpack(values), nrows, ncols,
+                                  sorted=sorted, name=name)
+
+
 def _torch_dtype(dt):
     import torch
 

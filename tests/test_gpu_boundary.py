@@ -433,3 +433,23 @@ def test_comparison_multiply_semirings(gb, dtype):
     both = xk[:, None] & bk
     assert np.array_equal(w2i, np.flatnonzero(both.any(axis=0)))
     assert np.array_equal(w2x, (~both | (xv[:, None] <= bv)).all(axis=0)[w2i])
+
+
+def test_dlpack_round_trip(gb):
+    """DLPack interop -- the library's device arrays out as capsules (zero-copy) and back in (copied)"""
+    import torch
+
+    rng = np.random.default_rng(41)
+    n = 500
+    idx = np.unique(rng.integers(0, n, 200))
+    v = gb.Vector.from_coo(idx, rng.random(idx.size), size=n)
+    cv, cp = gb.cuda.vector_to_dlpack(v)
+    tv, tp = torch.from_dlpack(cv), torch.from_dlpack(cp)
+    assert tv.is_cuda and tp.dtype == torch.uint8 and int(tp.sum()) == idx.size
+    w = gb.cuda.vector_from_dlpack(tv, tp)          # torch tensors speak __dlpack__
+    assert w.isequal(v)
+    r, c = H.random_coo(rng, 40, 30, 300)
+    A = gb.Matrix.from_coo(r, c, rng.integers(1, 9, r.size).astype(np.int64), nrows=40, ncols=30)
+    caps = gb.cuda.matrix_to_dlpack(A)
+    B = gb.cuda.matrix_from_dlpack(*[torch.from_dlpack(x) for x in caps], 40, 30)
+    assert B.isequal(A)

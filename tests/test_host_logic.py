@@ -80,3 +80,31 @@ def test_operator_strings_and_typed_lookup():
 
     assert _MULT_IDENTITY["times"](np.int64) == 1 and _MULT_IDENTITY["plus"](np.float32) == 0
     assert _MULT_IDENTITY["min"](np.int8) == 127 and _MULT_IDENTITY["max"](np.float64) == -np.inf and "pair" not in _MULT_IDENTITY
+
+
+def test_mxm_row_costs_and_partition():
+    """graphblas_b200/distributed.py: rows the split kernel hashes on several CTAs weigh more than their flops, rows that fit one table
+    do not; the cost-balanced prefix split is monotone, covers every row once and balances the weights."""
+    import numpy as np
+
+    from graphblas_b200 import distributed as D
+
+    f = np.array([0, 10, 10440, 10441, 40000, 100000], dtype=np.int64)
+    c = D.mxm_row_costs(f)
+    assert c[0] == 0 and c[1] == 10 and c[2] == 10440            # not split: cost = flops
+    parts = np.ceil(f * 1.125 / 16320)
+    assert np.allclose(c[3:], f[3:] * (1.0 + 1.0 * (parts[3:] - 1)))
+    assert np.array_equal(D.mxm_row_costs(f, reread=0.0), f.astype(np.float64))
+    import torch
+
+    assert np.allclose(D.mxm_row_costs(torch.tensor(f)).numpy(), c)
+    rng = np.random.default_rng(0)
+    flops = rng.integers(0, 3000, 5000)
+    flops[:20] = rng.integers(20000, 200000, 20)                 # heavy rows at the low indices, like an R-MAT matrix
+    cost = D.mxm_row_costs(flops)
+    prefix = np.concatenate([[0.0], np.cumsum(cost)])
+    for world in (2, 4, 8):
+        b = D.row_blocks_by_prefix(prefix, world)
+        assert b[0] == 0 and b[-1] == flops.size and all(x <= y for x, y in zip(b[:-1], b[1:]))
+        shares = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
+        assert shares.max() <= cost.sum() / world + cost.max() + 1
