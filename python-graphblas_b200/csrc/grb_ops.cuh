@@ -31,6 +31,33 @@ template <typename T> __host__ __device__ __forceinline__ T one_of() { return (T
 template <> __host__ __device__ __forceinline__ gbool one_of<gbool>() { return gbool(true); }
 
 // ---- generic typed binary op with a (possibly compile-time constant) op code ----
+// pow is a long routine (through double for the integer types): kept OUT of line on the device, because binop() is inlined
+// with a run-time opcode into every kernel that applies an accumulator or a dynamic semiring, and none of the hot paths uses it
+template <typename T> __host__ __device__ inline T pow_value(T x, T y) {
+    if constexpr (std::is_floating_point<T>::value) {
+        return (T)pow(x, y);
+    } else {
+        typedef typename std::make_unsigned<T>::type U;   // through double, saturating, NaN -> 0 (how SuiteSparse defines integer pow)
+        const double r = pow((double)x, (double)y);
+        if (r != r) return (T)0;
+        const T tmin = std::is_signed<T>::value ? (T)((U)1 << (sizeof(T) * 8 - 1)) : (T)0;
+        const T tmax = std::is_signed<T>::value ? (T)(~((U)1 << (sizeof(T) * 8 - 1))) : (T)~(U)0;
+        if (r <= (double)tmin) return tmin;
+        if (r >= (double)tmax) return tmax;
+        return (T)r;
+    }
+}
+#ifdef __CUDACC__
+template <typename T> __device__ __noinline__ T pow_out_of_line(T x, T y) { return pow_value<T>(x, y); }
+#endif
+template <typename T> __host__ __device__ __forceinline__ T pow_op(T x, T y) {
+#ifdef __CUDA_ARCH__
+    return pow_out_of_line<T>(x, y);
+#else
+    return pow_value<T>(x, y);
+#endif
+}
+
 template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T y) {
     if constexpr (is_gbool<T>::value) {
         switch (op) {
@@ -72,8 +99,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
-            case OP_POW: return (T)pow(x, y);
-            case OP_RPOW: return (T)pow(y, x);
+            case OP_POW: return pow_op<T>(x, y);
+            case OP_RPOW: return pow_op<T>(y, x);
         }
         return x;
     } else {
@@ -106,15 +133,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
-            case OP_POW: case OP_RPOW: {   // through double, saturating, NaN -> 0 (how SuiteSparse defines integer pow)
-                const double r = op == OP_POW ? pow((double)x, (double)y) : pow((double)y, (double)x);
-                if (r != r) return (T)0;
-                const T tmin = std::is_signed<T>::value ? (T)((U)1 << (sizeof(T) * 8 - 1)) : (T)0;
-                const T tmax = std::is_signed<T>::value ? (T)(~((U)1 << (sizeof(T) * 8 - 1))) : (T)~(U)0;
-                if (r <= (double)tmin) return tmin;
-                if (r >= (double)tmax) return tmax;
-                return (T)r;
-            }
+            case OP_POW: return pow_op<T>(x, y);
+            case OP_RPOW: return pow_op<T>(y, x);
         }
         return x;
     }
