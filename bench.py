@@ -160,6 +160,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU legs (reference arm and cpu_baseline)
+L2_NOTE = "no flush: every step streams inputs and outputs far larger than the 126 MB L2 (scale 22: 0.5 GB in, 20 GB out)"
 WORKLOAD = ("R-MAT scale-{scale} (0.45,0.15,0.15,0.25) ef16 seed42 A.mxm(A) plus_times fp32 [BASELINE configs[1], variant 2a]; "
             "CPU arm: random row sample of A times the full A per step, rate in nnz-out/s")
 
@@ -271,7 +272,7 @@ def run_reference(args):
         "impl": "reference", "metric": "mxm nnz-out/s (R-MAT plus_times fp32)", "value": value, "unit": "nnz-out/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(scale=scale)},
+        "config": {"workload": WORKLOAD.format(scale=scale), "l2": L2_NOTE},
         "cpu_baseline": {"value": value, "unit": "nnz-out/s", "cores": threads, "kind": "port", "sample": desc,
                          "note": "SuiteSparse unavailable -- baseline is the in-repo OpenMP SpGEMM (one pass, unsorted rows, hash / dense Gustavson accumulators)"},
         "e2e": {"value": value, "unit": "nnz-out/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -848,7 +849,7 @@ def run_ours(args):
         "metric": "mxm nnz-out/s (R-MAT plus_times fp32)", "value": value, "unit": "nnz-out/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(scale=scale)},
+        "config": {"workload": WORKLOAD.format(scale=scale), "l2": L2_NOTE},
         "problem": {"n": n, "nnz_A": nnz, "nnz_C": int(nnz_c), "flops": int(flops), "parallelism": f"row-partition x{world} (equal estimated cost: flops, split rows weighted), B replicated",
                     "l2": "inputs (0.5 GB) and outputs (>=GBs) exceed the 126 MB L2",
                     "result_form": "row-end CSR (rows in order, unused slots between rows where products merged), columns unsorted inside a row; "
