@@ -108,3 +108,46 @@ def test_mxm_row_costs_and_partition():
         assert b[0] == 0 and b[-1] == flops.size and all(x <= y for x, y in zip(b[:-1], b[1:]))
         shares = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
         assert shares.max() <= cost.sum() / world + cost.max() + 1
+
+
+def test_aggregator_recipes_name_ops_the_library_exports():
+    """graphblas_b200/agg.py (reference graphblas/core/operator/agg.py:347-534): every aggregator the reference defines outside its
+    `ss` namespace exists here, and every recipe step names a monoid / semiring / unary op that libgrb_cuda.so exports as a data
+    symbol for the types it is used with (symbol discovery needs no GPU)."""
+    from graphblas_b200 import agg
+    from graphblas_b200 import ffi as F
+
+    names = set(dir(F.__getattr__("lib")))
+    reference_aggs = ["sum", "prod", "all", "any", "min", "max", "any_value", "count", "count_nonzero", "count_zero", "sum_of_squares",
+                      "sum_of_inverses", "exists", "hypot", "logaddexp", "logaddexp2", "L0norm", "L1norm", "L2norm", "Linfnorm", "mean",
+                      "peak_to_peak", "varp", "vars", "stdp", "stds", "geometric_mean", "harmonic_mean", "root_mean_square"]
+    for n in reference_aggs:
+        assert isinstance(getattr(agg, n), agg.Aggregator), n
+    assert agg.L0norm is agg.count_nonzero and agg.L2norm is agg.hypot
+
+    def semiring_symbol(name, t):
+        add, mul = name.upper().split("_", 1)
+        mul = {"PAIR": "PAIR"}.get(mul, mul)
+        return [f"GrB_{add}_{mul}_SEMIRING_{t}", f"GxB_{add}_{mul}_{t}"]
+
+    for a in agg._ALL:
+        for sr in (a._semiring, a._semiring2):
+            if sr is None:
+                continue
+            for t in ("INT64", "FP64", "FP32"):
+                assert any(s in names for s in semiring_symbol(sr, t)), (a.name, sr, t)
+        if a._monoid is not None:
+            m = a._monoid.upper()
+            cands = [f"GrB_{m}_MONOID_FP64", f"GxB_{m}_FP64_MONOID", f"GrB_{m}_MONOID_BOOL", f"GxB_{m}_BOOL_MONOID"]
+            assert any(s in names for s in cands), (a.name, a._monoid)
+        for u in (a._applybegin, a._finalize):
+            if u is not None:
+                assert f"GrB_{u.upper()}_FP64" in names or f"GxB_{u.upper()}_FP64" in names, (a.name, u)
+        if a._composite is not None:
+            assert all(isinstance(p, agg.Aggregator) for p in a._composite) and a._combine is not None
+    # the ops the composite finalizers use
+    for s in ("GrB_DIV_FP64", "GrB_MINUS_FP64", "GxB_POW_FP64", "GxB_SQRT_FP64", "GrB_MINV_FP64", "GrB_IDENTITY_FP64", "GxB_PAIR_INT64"):
+        assert s in names, s
+    # comparison-multiply semirings and GrB_Matrix_diag (round 2)
+    for s in ("GxB_LOR_GT_INT32", "GxB_LAND_LE_FP64", "GxB_ANY_EQ_UINT8", "GxB_LOR_EQ_BOOL", "GxB_PLUS_ISGT_INT64", "GrB_Matrix_diag"):
+        assert s in names, s
