@@ -1,23 +1,24 @@
 // spgemm.cu -- T = A (+).(x) B for GrB_mxm: flop-binned hash SpGEMM (row-wise Gustavson), sm_100a.
 //
 //   row_flops : flops(i) = sum_{k in A(i,:)} nnz(B(k,:))   -- upper bound on nnz(T(i,:)); rows are binned by it.
-//   one-pass  (default when 2*flops*(4+s_val) bytes fit): every row is hashed ONCE, writing its entries into a
-//               staging CSR addressed by the flops prefix and recording the exact row count; an exclusive scan and a
-//               streaming compaction produce the final CSR.  No symbolic pass at all.
-//   two-pass  (memory-tight products, e.g. Graph500 skew): symbolic hash-set pass counts nnz per row, exact
-//               allocation, rows re-binned by nnz, numeric pass.
+//   one-pass  (default when the flops-sized arrays fit): every row is hashed ONCE and written into its own slots of arrays
+//               addressed by the flops prefix, its exact count recorded.  A product that hardly compresses (nnz(T) within 1/8 of
+//               the bound: the R-MAT squares) KEEPS those arrays as a row-end CSR (grb_internal.h CsrArrays::end) -- no copy;
+//               otherwise a scan and a streaming compaction produce the compact CSR at once.  No symbolic pass at all.
+//   two-pass  (memory-tight products, e.g. Graph500 skew): symbolic hash-set pass counts nnz per row, exact allocation, rows
+//               re-binned by nnz, numeric pass.
 //
-// Hash kernels.  Rows with <= 150 products: one warp per row, table in shared memory.  Larger rows: one CTA per
-// row; the A row is staged in shared memory a chunk at a time together with the start/length of every B row it
-// selects (one round trip per level of indirection for the whole chunk), the chunk's products are cut into work
-// items of 32 consecutive B entries, and 8-lane sub-groups pull items round-robin, issuing all loads of an item
-// before the first insert (no dependent chain per A entry, no straggler on a long B row).  Tables are sized per
-// row (1.6 x count, any size: multiply-shift range reduction instead of a power-of-two mask) inside the bin's
-// shared-memory allocation; rows beyond the largest shared table use global-memory tables.  For value types of
-// <= 4 bytes an entry is ONE 64-bit word (key:value) claimed by a single atomicCAS -- one shared-memory atomic per
-// product instead of two; accumulation into an existing key is an atomic monoid combine on the value half.
-// Rows come out unsorted ("jumbled"); sorting is lazy (structure.cu), as the reference's C library allows
-// (graphblas/core/matrix.py:1631-1644).
+// Hash kernels.  Rows with <= 150 products: one warp per row, table in shared memory (spgemm_warp_kernel).  Larger rows, unmasked
+// numeric: spgemm_rows_kernel -- persistent CTAs walk the bin's rows; the A row is staged in shared memory a chunk at a time
+// together with the start / length of every B row it selects, the chunk's products form one flat index space of which every warp
+// owns a contiguous range (128 products per step, one binary search, loads issued before the first insert); an entry is ONE 64-bit
+// word (key:value) claimed by a single atomicCAS for value types of <= 4 bytes; products that open a slot append it to a list kept
+// in the row's own output slots, and the drain walks that list (no table clear, no table scan).  Masked products, the symbolic
+// pass and the two-pass numeric phase use spgemm_block_kernel (CTA per row, clear + scan).  Tables are sized per row (2.5 x count,
+// any size: multiply-shift range reduction instead of a power-of-two mask) inside the bin's shared-memory allocation; rows beyond
+// the largest shared table are SPLIT over several CTAs by a second hash of the column (each part fits a shared table), or -- under
+// a mask -- use global-memory tables.  Rows come out unsorted ("jumbled"); sorting is lazy (structure.cu), as the reference's C
+// library allows (graphblas/core/matrix.py:1631-1644).
 //
 // Serves GrB_mxm: reference graphblas/core/matrix.py:2319-2328 (call assembled at core/base.py:496-503).
 #include <cub/cub.cuh>
