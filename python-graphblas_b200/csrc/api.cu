@@ -29,7 +29,9 @@ static GrB_Info mat_vec_common(GrB_Vector w, const GrB_Vector mask, const GrB_Bi
     }
     const PeerTargets *peer = g_peer.n > 0 ? &g_peer : nullptr;
     const bool needs_epi = mask != nullptr || accum != nullptr || comp || peer;
-    const bool can_fuse = needs_epi && w->type == op->type && (!accum || (accum->type == w->type && accum->ztype == accum->type)) &&
+    // (a pow accumulator takes the separate write-back pass: the fused epilogue is compiled without pow, grb_ops.cuh binop<T, false>)
+    const bool can_fuse = needs_epi && w->type == op->type &&
+                          (!accum || (accum->type == w->type && accum->ztype == accum->type && accum->opcode != OP_POW && accum->opcode != OP_RPOW)) &&
                           (peer || opt_get_int("fuse_epilogue", 1) != 0);
     if (peer && !can_fuse) {
         dev_free(mtmp);

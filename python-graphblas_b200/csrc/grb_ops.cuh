@@ -58,7 +58,10 @@ template <typename T> __host__ __device__ __forceinline__ T pow_op(T x, T y) {
 #endif
 }
 
-template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T y) {
+// WITH_POW = false: the same switch without pow -- for the accumulator fused into the SpMV kernels (spmv_common.cuh epi_write; the
+// host never fuses a pow accumulator): with pow in it the int64 segmented kernel spilled 56 bytes and the masked pull went from 32 to 48
+// registers (cuobjdump --dump-resource-usage), an SSSP sweep from 0.745 to 0.84 ms
+template <typename T, bool WITH_POW = true> __host__ __device__ __forceinline__ T binop(int op, T x, T y) {
     if constexpr (is_gbool<T>::value) {
         switch (op) {
             case OP_FIRST: case OP_DIV: return x;
@@ -99,8 +102,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
-            case OP_POW: return pow_op<T>(x, y);
-            case OP_RPOW: return pow_op<T>(y, x);
+            case OP_POW: if constexpr (WITH_POW) return pow_op<T>(x, y); else break;
+            case OP_RPOW: if constexpr (WITH_POW) return pow_op<T>(y, x); else break;
         }
         return x;
     } else {
@@ -133,8 +136,8 @@ template <typename T> __host__ __device__ __forceinline__ T binop(int op, T x, T
             case OP_LT: return (T)(x < y);
             case OP_GE: return (T)(x >= y);
             case OP_LE: return (T)(x <= y);
-            case OP_POW: return pow_op<T>(x, y);
-            case OP_RPOW: return pow_op<T>(y, x);
+            case OP_POW: if constexpr (WITH_POW) return pow_op<T>(x, y); else break;
+            case OP_RPOW: if constexpr (WITH_POW) return pow_op<T>(y, x); else break;
         }
         return x;
     }

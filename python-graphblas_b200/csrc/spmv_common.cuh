@@ -78,7 +78,7 @@ __device__ __forceinline__ void epi_write(const VecEpi<T> &e, int64_t row, T t, 
     T z = t;
     bool zp = tp != 0;
     if (e.accum != OP_NONE && cp) {
-        z = zp ? binop<T>(e.accum, c, z) : c;
+        z = zp ? binop<T, false>(e.accum, c, z) : c;   // no pow here (api.cu never fuses a pow accumulator): keeps the hot kernels lean
         zp = true;
     }
     if (!m) {
